@@ -1,0 +1,21 @@
+"""atq -- B200-native (sm_100a) drop-in for the `atq` package of ak736/ATQ-Multimodal.
+
+Same public names and signatures as the reference's atq/__init__.py:2-12; every tensor op
+runs in hand-written CUDA kernels reached through the C ABI of libatq_sm100.so
+(include/atq_sm100.h).  There is no CPU path: CPU tensors raise RuntimeError and a missing
+library raises ImportError at import time.
+"""
+from . import _native  # noqa: F401  (loads libatq_sm100.so; ImportError if it was not built)
+from .quantizers import adaptive_ternary_quantization
+from .layers import TernaryLinear
+from .routing import apply_selective_routing, SelectiveGradientRouting
+from .precision_boost import ResidualPrecisionBoostLinear
+from ._engine import set_gemm_mode, get_gemm_mode, set_ste
+
+__all__ = [
+    'adaptive_ternary_quantization',
+    'TernaryLinear',
+    'SelectiveGradientRouting',
+    'apply_selective_routing',
+    'ResidualPrecisionBoostLinear',
+]

@@ -1,0 +1,398 @@
+"""Host-side runtime of the ATQ hot path on B200: tensor-level wrappers over the C ABI,
+the per-layer quantization cache, and the autograd nodes that reproduce the reference's
+gradient contract:
+
+  TernaryLinear : dX = dY (alpha T);  d(alpha) = sum(G .* T);  d(bias);  weight.grad stays None
+  RPB           : dX = dY Wm;  dW = G .* mask;  d(alpha) = sum(G .* T .* (1-mask));  d(bias)
+
+with G = dY^T X.  A true straight-through estimator (dW = G for TernaryLinear) is opt-in
+(`atq.set_ste(True)`), off by default, and never used by the parity tests.
+
+GEMM precision modes: "parity" (default) feeds every fp32 operand as a bf16 hi+lo
+pair (2-3 tcgen05.mma terms into one TMEM accumulator; matches the fp32 reference within
+rtol 1e-2 / atol 1e-3); "fast" uses the hi term only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import _native as nv
+
+_MODE = os.environ.get("ATQ_GEMM_MODE", "parity")
+_STE = os.environ.get("ATQ_STE", "0") == "1"
+
+
+def set_gemm_mode(mode: str) -> None:
+    global _MODE
+    if mode not in ("parity", "fast"):
+        raise ValueError("mode must be 'parity' or 'fast'")
+    _MODE = mode
+
+
+def get_gemm_mode() -> str:
+    return _MODE
+
+
+def set_ste(enabled: bool) -> None:
+    global _STE
+    _STE = bool(enabled)
+
+
+def _use_lo() -> bool:
+    return _MODE == "parity"
+
+
+# ---------------------------------------------------------------------------------------
+# tensor-level ops
+# ---------------------------------------------------------------------------------------
+
+def threshold_index(numel: int, sparsity_target) -> int:
+    # atq/quantizers.py:28 -- Python double arithmetic, truncation toward zero
+    return int(sparsity_target * numel)
+
+
+def adaptive_threshold(w: torch.Tensor, sparsity_target, threshold_factor=0.05) -> torch.Tensor:
+    """0-dim fp32 CUDA tensor holding the layer threshold (A1); no host sync."""
+    w = nv.require_f32(w, "weights")
+    dev = nv.device_index(w)
+    n = w.numel()
+    k = threshold_index(n, sparsity_target)
+    thr = torch.empty((), dtype=torch.float32, device=w.device)
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_adaptive_threshold(n), w.device)
+    nv.call("atq_adaptive_threshold", dev, w.data_ptr(), n, k, float(threshold_factor), thr.data_ptr(),
+            ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+    return thr
+
+
+def adaptive_threshold_batched(weights, sparsity_targets, threshold_factor=0.05):
+    """Thresholds of many layers in one launch sequence.  Returns a [count] fp32 tensor."""
+    count = len(weights)
+    ws_list = [nv.require_f32(w, "weights") for w in weights]
+    dev = nv.device_index(ws_list[0])
+    thr = torch.empty(count, dtype=torch.float32, device=ws_list[0].device)
+    n_arr = (ctypes.c_int64 * count)(*[w.numel() for w in ws_list])
+    k_arr = (ctypes.c_int64 * count)(*[threshold_index(w.numel(), s) for w, s in zip(ws_list, sparsity_targets)])
+    w_arr = (ctypes.c_void_p * count)(*[w.data_ptr() for w in ws_list])
+    t_arr = (ctypes.c_void_p * count)(*[thr.data_ptr() + 4 * i for i in range(count)])
+    wsb = nv.workspace(nv.lib.atq_workspace_bytes_adaptive_threshold_batched(count, n_arr), thr.device)
+    nv.call("atq_adaptive_threshold_batched", dev, count, w_arr, n_arr, k_arr, float(threshold_factor), t_arr,
+            wsb.data_ptr(), wsb.numel(), nv.stream_ptr(dev))
+    return thr
+
+
+def select_kth_abs(x: torch.Tensor, k: int) -> torch.Tensor:
+    x = nv.require_f32(x, "input")
+    dev = nv.device_index(x)
+    n = x.numel()
+    thr = torch.empty((), dtype=torch.float32, device=x.device)
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_select_kth_abs(n), x.device)
+    nv.call("atq_select_kth_abs", dev, x.data_ptr(), n, int(k), thr.data_ptr(), ws.data_ptr(), ws.numel(),
+            nv.stream_ptr(dev))
+    return thr
+
+
+def ternarize_f32(w: torch.Tensor, thr: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    w = nv.require_f32(w, "weights")
+    dev = nv.device_index(w)
+    t = torch.empty_like(w)
+    nv.call("atq_ternarize_f32", dev, w.data_ptr(), w.numel(), thr.data_ptr(), t.data_ptr(), nv.ptr(stats),
+            nv.stream_ptr(dev))
+    return t
+
+
+def ternarize_pack2(w: torch.Tensor, thr: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    w = nv.require_f32(w, "weights")
+    dev = nv.device_index(w)
+    n = w.numel()
+    packed = torch.empty((n + 3) // 4, dtype=torch.uint8, device=w.device)
+    nv.call("atq_ternarize_pack2", dev, w.data_ptr(), n, thr.data_ptr(), packed.data_ptr(), nv.ptr(stats),
+            nv.stream_ptr(dev))
+    return packed
+
+
+def optimal_alpha(w: torch.Tensor, tern_stats: torch.Tensor) -> torch.Tensor:
+    """alpha* of atq/quantizers.py:46-55 from the ternarize statistics (device-resolved branch)."""
+    dev = nv.device_index(w)
+    abs_stats = torch.empty(16, dtype=torch.uint8, device=w.device)
+    nv.call("atq_abs_stats", dev, w.data_ptr(), w.numel(), abs_stats.data_ptr(), None, 0, nv.stream_ptr(dev))
+    alpha = torch.empty((), dtype=torch.float32, device=w.device)
+    nv.call("atq_optimal_alpha", dev, tern_stats.data_ptr(), abs_stats.data_ptr(), w.numel(), alpha.data_ptr(),
+            nv.stream_ptr(dev))
+    return alpha
+
+
+def pack2_from_f32(t: torch.Tensor):
+    t = nv.require_f32(t, "ternary_weights")
+    dev = nv.device_index(t)
+    n = t.numel()
+    packed = torch.empty((n + 3) // 4, dtype=torch.uint8, device=t.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=t.device)
+    if n > 0:
+        nv.call("atq_pack2_from_f32", dev, t.data_ptr(), n, packed.data_ptr(), flag.data_ptr(), nv.stream_ptr(dev))
+    return packed, flag
+
+
+def unpack2(packed: torch.Tensor, n: int, dtype=torch.float32, flag: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if packed.dtype != torch.uint8:
+        raise RuntimeError("atq: packed_weights must be uint8")
+    dev = nv.device_index(packed)
+    packed = packed.contiguous()
+    if packed.numel() < (n + 3) // 4:
+        raise RuntimeError("atq: packed_weights too short for num_values")
+    out = torch.empty(n, dtype=dtype, device=packed.device)
+    if n == 0:
+        return out
+    if dtype == torch.float32:
+        nv.call("atq_unpack2_to_f32", dev, packed.data_ptr(), n, out.data_ptr(), nv.ptr(flag), nv.stream_ptr(dev))
+    elif dtype == torch.bfloat16:
+        nv.call("atq_unpack2_to_bf16", dev, packed.data_ptr(), n, out.data_ptr(), nv.stream_ptr(dev))
+    elif dtype == torch.int8:
+        nv.call("atq_unpack2_to_i8", dev, packed.data_ptr(), n, out.data_ptr(), nv.stream_ptr(dev))
+    else:
+        raise RuntimeError(f"atq: unsupported unpack dtype {dtype}")
+    return out
+
+
+def route_mask_mul(x: torch.Tensor, grad_out: torch.Tensor, thr: torch.Tensor) -> torch.Tensor:
+    x = nv.require_f32(x, "input")
+    g = nv.require_f32(grad_out, "grad_output")
+    dev = nv.device_index(x)
+    out = torch.empty_like(g)
+    if x.numel():
+        nv.call("atq_route_mask_mul", dev, x.data_ptr(), g.data_ptr(), thr.data_ptr(), x.numel(), out.data_ptr(),
+                nv.stream_ptr(dev))
+    return out
+
+
+def split_bf16(x2: torch.Tensor, want_lo: bool):
+    """fp32 [rows, cols] -> (hi, lo|None, pitch) bf16 row-major."""
+    rows, cols = x2.shape
+    dev = nv.device_index(x2)
+    pitch = nv.round_up(cols, 8)
+    hi = torch.empty((rows, pitch), dtype=torch.bfloat16, device=x2.device)
+    lo = torch.empty((rows, pitch), dtype=torch.bfloat16, device=x2.device) if want_lo else None
+    nv.call("atq_split_bf16", dev, x2.data_ptr(), rows, cols, x2.stride(0), hi.data_ptr(), nv.ptr(lo), pitch,
+            nv.stream_ptr(dev))
+    return hi, lo, pitch
+
+
+def split_bf16_t(x2: torch.Tensor, want_lo: bool):
+    """fp32 [rows, cols] -> transposed (hi_t, lo_t|None, pitch_t), each [cols, pitch_t]."""
+    rows, cols = x2.shape
+    dev = nv.device_index(x2)
+    pitch_t = nv.round_up(rows, 8)
+    hi = torch.empty((cols, pitch_t), dtype=torch.bfloat16, device=x2.device)
+    lo = torch.empty((cols, pitch_t), dtype=torch.bfloat16, device=x2.device) if want_lo else None
+    nv.call("atq_split_bf16_t", dev, x2.data_ptr(), rows, cols, x2.stride(0), hi.data_ptr(), nv.ptr(lo), pitch_t,
+            None, nv.stream_ptr(dev))
+    return hi, lo, pitch_t
+
+
+def colsum(x2: torch.Tensor) -> torch.Tensor:
+    rows, cols = x2.shape
+    dev = nv.device_index(x2)
+    out = torch.empty(cols, dtype=torch.float32, device=x2.device)
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_colsum(rows, cols), x2.device)
+    nv.call("atq_colsum_f32", dev, x2.data_ptr(), rows, cols, x2.stride(0), out.data_ptr(), ws.data_ptr(), ws.numel(),
+            nv.stream_ptr(dev))
+    return out
+
+
+def tgemm(a, b, rows: int, cols: int, kdim: int, scale=None, bias=None, dot_ref=None):
+    """out[rows, cols] = scale * (A . B^T) + bias;  a, b = (hi, lo|None, pitch).
+    With dot_ref (fp32 [rows, cols]) also returns sum(acc .* dot_ref) as a [1] tensor."""
+    hi = a[0]
+    dev = nv.device_index(hi)
+    out = torch.empty((rows, cols), dtype=torch.float32, device=hi.device)
+    oa, ob = nv.operand(*a), nv.operand(*b)
+    dot_out = torch.empty(1, dtype=torch.float32, device=hi.device) if dot_ref is not None else None
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_tgemm(rows, cols) if dot_ref is not None else 0, hi.device)
+    nv.call("atq_tgemm", dev, rows, cols, kdim, ctypes.byref(oa), ctypes.byref(ob), nv.ptr(scale), nv.ptr(bias),
+            out.data_ptr(), cols, nv.ptr(dot_ref), 0 if dot_ref is None else dot_ref.stride(0), nv.ptr(dot_out),
+            ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+    return out, dot_out
+
+
+def tgemm_dw_masked(dy_t, x_t, m_out: int, k_in: int, n_tok: int, mask=None, packed=None):
+    hi = dy_t[0]
+    dev = nv.device_index(hi)
+    dw = torch.empty((m_out, k_in), dtype=torch.float32, device=hi.device)
+    oa, ob = nv.operand(*dy_t), nv.operand(*x_t)
+    dalpha = torch.empty(1, dtype=torch.float32, device=hi.device) if packed is not None else None
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_tgemm(m_out, k_in) if packed is not None else 0, hi.device)
+    nv.call("atq_tgemm_dw_masked", dev, m_out, k_in, n_tok, ctypes.byref(oa), ctypes.byref(ob), nv.ptr(mask),
+            nv.ptr(packed), dw.data_ptr(), k_in, nv.ptr(dalpha), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+    return dw, dalpha
+
+
+# ---------------------------------------------------------------------------------------
+# per-layer quantization cache: everything the GEMMs consume, rebuilt only when
+# the weight / alpha / mask tensors or the sparsity target changed.
+# ---------------------------------------------------------------------------------------
+
+class LayerOperands:
+    __slots__ = ("key", "thr", "packed", "w", "w_t", "packed_flat_ok")
+
+    def __init__(self):
+        self.key = None
+        self.thr = None
+        self.packed = None
+        self.w = None      # (hi, lo|None, pitch)   [M, pitch]  forward B operand
+        self.w_t = None    # (hi, lo|None, pitch_t) [K, pitch_t] dX B operand
+
+
+def _key(weight, alpha, mask, sparsity_target, threshold_factor):
+    return (weight.data_ptr(), weight._version, tuple(weight.shape),
+            None if alpha is None else (alpha.data_ptr(), alpha._version),
+            None if mask is None else (mask.data_ptr(), mask._version),
+            float(sparsity_target), float(threshold_factor), _MODE)
+
+
+@torch.no_grad()
+def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, threshold_factor=0.05,
+                   thr: Optional[torch.Tensor] = None) -> LayerOperands:
+    """mask None -> TernaryLinear operands (T exact in bf16; alpha applied in the GEMM epilogue).
+    mask given -> RPB mixed weight Wm = T*alpha*(1-mask) + W*mask as bf16 hi/lo."""
+    key = _key(weight, alpha if mask is not None else None, mask, sparsity_target, threshold_factor)
+    if cache.key == key:
+        return cache
+    w = nv.require_f32(weight.detach(), "weight")
+    dev = nv.device_index(w)
+    M, K = w.shape
+    if thr is None:
+        thr = adaptive_threshold(w, sparsity_target, threshold_factor)
+    pitch, pitch_t = nv.round_up(K, 8), nv.round_up(M, 8)
+    n = M * K
+    want_lo = _use_lo() and mask is not None
+    bf = torch.bfloat16
+    hi = torch.empty((M, pitch), dtype=bf, device=w.device)
+    hi_t = torch.empty((K, pitch_t), dtype=bf, device=w.device)
+    lo = torch.empty((M, pitch), dtype=bf, device=w.device) if want_lo else None
+    lo_t = torch.empty((K, pitch_t), dtype=bf, device=w.device) if want_lo else None
+    packed = torch.empty((n + 3) // 4, dtype=torch.uint8, device=w.device)
+    flat_ok = (K % 4 == 0)
+    st = nv.stream_ptr(dev)
+    if mask is None:
+        nv.call("atq_build_ternary_operands", dev, w.data_ptr(), M, K, thr.data_ptr(),
+                packed.data_ptr() if flat_ok else None, hi.data_ptr(), pitch, hi_t.data_ptr(), pitch_t, None, st)
+    else:
+        mk = nv.require_f32(mask, "precision_mask")
+        al = nv.require_f32(alpha.detach(), "alpha")
+        nv.call("atq_build_mixed_operands", dev, w.data_ptr(), mk.data_ptr(), M, K, thr.data_ptr(), al.data_ptr(),
+                packed.data_ptr() if flat_ok else None, hi.data_ptr(), nv.ptr(lo), pitch, hi_t.data_ptr(),
+                nv.ptr(lo_t), pitch_t, st)
+    if not flat_ok:  # rows of the flat codec do not start on byte boundaries
+        nv.call("atq_ternarize_pack2", dev, w.data_ptr(), n, thr.data_ptr(), packed.data_ptr(), None, st)
+    cache.key, cache.thr, cache.packed = key, thr, packed
+    cache.w, cache.w_t = (hi, lo, pitch), (hi_t, lo_t, pitch_t)
+    return cache
+
+
+# ---------------------------------------------------------------------------------------
+# autograd nodes
+# ---------------------------------------------------------------------------------------
+
+class _TernaryLinearFn(torch.autograd.Function):
+    """y = x (alpha T)^T + b   (atq/layers.py:35-43)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, alpha, bias, ops: LayerOperands):
+        M, K = weight.shape
+        x2 = nv.require_f32(x, "input").reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        N = x2.shape[0]
+        al = alpha.detach()
+        if N == 0:
+            y = x2.new_zeros((0, M))
+        else:
+            xa = split_bf16(x2, _use_lo())
+            y, _ = tgemm(xa, ops.w, N, M, K, scale=al, bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(x2, al)
+        ctx.ops_w_t = ops.w_t
+        ctx.has_bias = bias is not None
+        ctx.wshape = (M, K)
+        ctx.xshape = x.shape
+        ctx.ste = _STE
+        return y.reshape(*x.shape[:-1], M)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, al = ctx.saved_tensors
+        M, K = ctx.wshape
+        N = x2.shape[0]
+        g2 = nv.require_f32(gy, "grad_output").reshape(-1, M)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        if N == 0:
+            return (gy.new_zeros(ctx.xshape), None, al.new_zeros(1), g2.new_zeros(M) if ctx.has_bias else None, None)
+        ga = split_bf16(g2, _use_lo())
+        # dX = alpha * (dY . T);  d(alpha) = sum((dY . T) .* X) fused in the same epilogue
+        dx, dalpha = tgemm(ga, ctx.ops_w_t, N, K, M, scale=al, dot_ref=x2)
+        dbias = colsum(g2) if ctx.has_bias else None
+        dw = None
+        if ctx.ste:  # opt-in straight-through estimator: dW = G
+            gt, xt = split_bf16_t(g2, _use_lo()), split_bf16_t(x2, _use_lo())
+            dw, _ = tgemm_dw_masked(gt, xt, M, K, N)
+        return dx.reshape(ctx.xshape), dw, dalpha, dbias, None
+
+
+class _RPBLinearFn(torch.autograd.Function):
+    """y = x Wm^T + b,  Wm = T*alpha*(1-mask) + W*mask   (atq/precision_boost.py:62-74)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, alpha, bias, mask, ops: LayerOperands):
+        M, K = weight.shape
+        x2 = nv.require_f32(x, "input").reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        N = x2.shape[0]
+        if N == 0:
+            y = x2.new_zeros((0, M))
+        else:
+            xa = split_bf16(x2, _use_lo())
+            y, _ = tgemm(xa, ops.w, N, M, K, scale=None, bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(x2, mask)
+        ctx.ops_w_t, ctx.packed = ops.w_t, ops.packed
+        ctx.has_bias = bias is not None
+        ctx.wshape = (M, K)
+        ctx.xshape = x.shape
+        return y.reshape(*x.shape[:-1], M)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, mask = ctx.saved_tensors
+        M, K = ctx.wshape
+        N = x2.shape[0]
+        g2 = nv.require_f32(gy, "grad_output").reshape(-1, M)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        if N == 0:
+            z = g2.new_zeros
+            return (gy.new_zeros(ctx.xshape), z((M, K)), z(1), z(M) if ctx.has_bias else None, None, None)
+        lo = _use_lo()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            ga = split_bf16(g2, lo)
+            dx, _ = tgemm(ga, ctx.ops_w_t, N, K, M)
+            dx = dx.reshape(ctx.xshape)
+        # G = dY^T X with the mask and the d(alpha) reduction fused into the epilogue
+        gt, xt = split_bf16_t(g2, lo), split_bf16_t(x2, lo)
+        mk = mask if mask.is_contiguous() else mask.contiguous()
+        dw, dalpha = tgemm_dw_masked(gt, xt, M, K, N, mask=mk, packed=ctx.packed)
+        dbias = colsum(g2) if ctx.has_bias else None
+        return dx, dw, dalpha, dbias, None, None
+
+
+def ternary_linear(x, weight, alpha, bias, cache: LayerOperands, sparsity_target=0.3, threshold_factor=0.05):
+    ops = layer_operands(cache, weight, None, None, sparsity_target, threshold_factor)
+    return _TernaryLinearFn.apply(x, weight, alpha, bias, ops)
+
+
+def rpb_linear(x, weight, alpha, bias, mask, cache: LayerOperands, sparsity_target=0.3, threshold_factor=0.05):
+    ops = layer_operands(cache, weight, alpha, mask, sparsity_target, threshold_factor)
+    return _RPBLinearFn.apply(x, weight, alpha, bias, mask, ops)

@@ -1,0 +1,142 @@
+"""ctypes binding of libatq_sm100.so (the C ABI declared in include/atq_sm100.h).
+
+There is no CPU fallback and no alternative backend: importing this module without the built
+library raises ImportError, and every wrapper raises RuntimeError for tensors that are not
+contiguous fp32 CUDA tensors on an sm_100-class device.  PyTorch is used here only for device
+memory (the caching allocator owns every buffer, including workspaces) and for the current
+stream handle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libatq_sm100.so")
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C atq-multimodal_b200/csrc`). The atq package has no CPU or eager fallback.")
+_lib = ctypes.CDLL(_LIB_PATH)
+
+ABI_VERSION = 1
+
+
+class BF16Operand(Structure):
+    _fields_ = [("hi", c_void_p), ("lo", c_void_p), ("pitch", c_int64)]
+
+
+_P = c_void_p
+_SIGS = {
+    "atq_abi_version": (c_int, []),
+    "atq_last_error_string": (c_char_p, []),
+    "atq_device_check": (c_int, [c_int]),
+    "atq_num_sms": (c_int, [c_int]),
+    "atq_workspace_bytes_abs_stats": (c_size_t, [c_int64]),
+    "atq_abs_stats": (c_int, [c_int, _P, c_int64, _P, _P, c_size_t, _P]),
+    "atq_workspace_bytes_select_kth_abs": (c_size_t, [c_int64]),
+    "atq_select_kth_abs": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "atq_workspace_bytes_adaptive_threshold": (c_size_t, [c_int64]),
+    "atq_adaptive_threshold": (c_int, [c_int, _P, c_int64, c_int64, c_float, _P, _P, c_size_t, _P]),
+    "atq_workspace_bytes_adaptive_threshold_batched": (c_size_t, [c_int, POINTER(c_int64)]),
+    "atq_adaptive_threshold_batched": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64),
+                                               c_float, POINTER(c_void_p), _P, c_size_t, _P]),
+    "atq_ternarize_f32": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P]),
+    "atq_ternarize_pack2": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P]),
+    "atq_optimal_alpha": (c_int, [c_int, _P, _P, c_int64, _P, _P]),
+    "atq_pack2_from_f32": (c_int, [c_int, _P, c_int64, _P, _P, _P]),
+    "atq_unpack2_to_f32": (c_int, [c_int, _P, c_int64, _P, _P, _P]),
+    "atq_unpack2_to_bf16": (c_int, [c_int, _P, c_int64, _P, _P]),
+    "atq_unpack2_to_i8": (c_int, [c_int, _P, c_int64, _P, _P]),
+    "atq_route_mask_mul": (c_int, [c_int, _P, _P, _P, c_int64, _P, _P]),
+    "atq_split_bf16": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
+    "atq_split_bf16_t": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P]),
+    "atq_build_ternary_operands": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int64, _P, _P]),
+    "atq_build_mixed_operands": (c_int, [c_int, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P,
+                                         c_int64, _P]),
+    "atq_workspace_bytes_tgemm": (c_size_t, [c_int64, c_int64]),
+    "atq_tgemm": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P, _P,
+                          c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
+    "atq_tgemm_fwd": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P,
+                              _P, c_int64, _P, c_size_t, _P]),
+    "atq_tgemm_dx": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P,
+                             c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
+    "atq_tgemm_dw_masked": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P,
+                                    _P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "atq_workspace_bytes_colsum": (c_size_t, [c_int64, c_int64]),
+    "atq_colsum_f32": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(_lib, _name)  # AttributeError here = header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if _lib.atq_abi_version() != ABI_VERSION:
+    raise ImportError(f"libatq_sm100.so ABI {_lib.atq_abi_version()} != binding ABI {ABI_VERSION}; rebuild")
+
+lib = _lib
+_checked_devices: set = set()
+gpu_launches = 0  # number of library compute calls issued (bench.py reports it)
+
+
+class ATQNativeError(RuntimeError):
+    pass
+
+
+def last_error() -> str:
+    s = _lib.atq_last_error_string()
+    return s.decode() if s else ""
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise ATQNativeError(f"{what} failed with status {status}: {last_error()}")
+
+
+def device_index(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("atq (B200 build) only runs on CUDA tensors: there is no CPU fallback; "
+                           f"got a tensor on {t.device}")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _checked_devices:
+        check(_lib.atq_device_check(idx), "atq_device_check")
+        _checked_devices.add(idx)
+    return idx
+
+
+def require_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"atq: {name} must be float32, got {t.dtype}")
+    device_index(t)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def stream_ptr(dev: int) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    # the caching allocator makes this a free-list pop; stream-ordered reuse is handled by torch
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def call(name: str, *args) -> None:
+    global gpu_launches
+    gpu_launches += 1
+    check(getattr(_lib, name)(*args), name)
+
+
+def operand(hi: torch.Tensor, lo, pitch: int) -> BF16Operand:
+    return BF16Operand(hi.data_ptr(), None if lo is None else lo.data_ptr(), pitch)

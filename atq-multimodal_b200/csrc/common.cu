@@ -1,0 +1,70 @@
+// Library-level plumbing of libatq_sm100: error text, device selection, device checks.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace atq {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_cur_device = -1;
+static int g_sm_count[64] = {0};
+
+char* last_error_buf() { return g_err; }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ensure_device(int device) {
+  if (device < 0 || device >= 64) {
+    set_error("bad device index %d", device);
+    return ATQ_EINVAL;
+  }
+  if (g_cur_device != device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+      set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+      return ATQ_ECUDA;
+    }
+    g_cur_device = device;
+  }
+  return ATQ_OK;
+}
+
+int sm_count(int device) {
+  if (device < 0 || device >= 64) return kNumSMsB200;
+  if (g_sm_count[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0) v = kNumSMsB200;
+    g_sm_count[device] = v;
+  }
+  return g_sm_count[device];
+}
+
+}  // namespace atq
+
+extern "C" {
+
+int atq_abi_version(void) { return 1; }
+
+const char* atq_last_error_string(void) { return atq::last_error_buf(); }
+
+int atq_device_check(int device) {
+  int major = 0, minor = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess) {
+    atq::set_error("atq_device_check: cannot query device %d", device);
+    return ATQ_ECUDA;
+  }
+  if (major != 10) {
+    atq::set_error("atq_device_check: device %d is sm_%d%d; this library is sm_100a only", device, major, minor);
+    return ATQ_EARCH;
+  }
+  return ATQ_OK;
+}
+
+int atq_num_sms(int device) { return atq::sm_count(device); }
+
+}  // extern "C"

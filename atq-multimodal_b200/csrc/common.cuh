@@ -1,0 +1,110 @@
+// Shared helpers for libatq_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/atq_sm100.h"
+
+namespace atq {
+
+constexpr int kNumSMsB200 = 148;
+
+// thread-local last-error text (atq_last_error_string)
+char* last_error_buf();
+void set_error(const char* fmt, ...);
+
+// Make `device` current on the calling thread (autograd's backward thread starts on device 0
+// from this library's statically linked runtime's point of view).
+int ensure_device(int device);
+int sm_count(int device);
+
+#define ATQ_CHECK_ARG(cond, msg)                                   \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      atq::set_error("%s: %s", __func__, msg);                     \
+      return ATQ_EINVAL;                                           \
+    }                                                              \
+  } while (0)
+
+#define ATQ_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      atq::set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__));     \
+      return ATQ_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define ATQ_LAUNCH_CHECK()                                                               \
+  do {                                                                                   \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      atq::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
+      return ATQ_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define ATQ_ENSURE_DEVICE(dev)              \
+  do {                                      \
+    int r__ = atq::ensure_device(dev);      \
+    if (r__ != ATQ_OK) return r__;          \
+  } while (0)
+
+// grid for a grid-stride streaming kernel: enough CTAs to cover `work_items` once at
+// `per_cta` items each, capped at `waves` resident CTAs per SM, rounded to a multiple of the
+// SM count when capped.
+inline int stream_grid(int device, int64_t work_items, int per_cta, int ctas_per_sm) {
+  int64_t need = (work_items + per_cta - 1) / per_cta;
+  int64_t cap = (int64_t)sm_count(device) * ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  // read-once streaming data: keep it out of L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 2-bit code of the reference codec (atq/bit_packing.py:49): value+1 -> {0,1,2}
+__device__ __forceinline__ uint32_t tern_code(float w, float thr) {
+  // strict compares as atq/quantizers.py:42-43; NaN compares false both ways -> code 1 (zero)
+  return (w > thr) ? 2u : ((w < -thr) ? 0u : 1u);
+}
+
+__device__ __forceinline__ uint16_t bf16_bits(float f) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) {
+  return __uint_as_float(((uint32_t)b) << 16);
+}
+// hi = bf16(x); lo = bf16(x - hi) (0 when hi is not finite)
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+  hi = bf16_bits(x);
+  float hf = bf16_bits_to_float(hi);
+  float r = x - hf;
+  lo = (fabsf(hf) <= 3.3895313892515355e38f) ? bf16_bits(r) : (uint16_t)0;
+}
+
+}  // namespace atq

@@ -1,0 +1,552 @@
+// Ternary GEMMs for B200: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+//   D[rows, cols] = sum_terms A_t[rows, kdim] . B_t[cols, kdim]^T      (fp32 accumulate in TMEM)
+//
+// Both operands are K-major bf16 tiles fetched by TMA into 128-byte-swizzled shared memory.
+// fp32 activations / gradients arrive as a bf16 (hi, lo) pair (x = hi + lo to ~16 mantissa
+// bits): the MMA warp issues one tcgen05.mma per term (hi*hi, lo*hi, hi*lo) into the SAME
+// TMEM accumulator, which is what keeps the result inside rtol 1e-2 / atol 1e-3 of the
+// reference's fp32 F.linear.  Ternary weights are exact in bf16.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (TMEM -> registers -> global) with the layer's
+// epilogue fused: alpha scale, bias, routing/precision mask, d(alpha) reduction.
+//
+// Replaces: F.linear in atq/layers.py:43 and atq/precision_boost.py:74, the unpack-then-matmul
+// of atq/bit_packing.py:165-176, and autograd's two backward GEMMs for those nodes.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace atq {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBudget = 227 * 1024 - 2048;
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "n"(NCOLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_smem_desc_kmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address  [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused with swizzle) [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset = 1024 B  [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: kind::f16, A=B=bf16, D=f32, both K-major, M=128, N=BLOCK_N
+template <int BLOCK_N>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+enum { EPI_LINEAR = 0, EPI_MASKED = 1 };
+
+struct GemmParams {
+  int64_t rows, cols, kdim;
+  float* out;
+  int64_t out_pitch;
+  const float* scale;     // device scalar, nullable           (LINEAR)
+  const float* bias;      // [cols], nullable                   (LINEAR)
+  const float* dot_ref;   // fp32 [rows, dot_ref_pitch], nullable (LINEAR): partial += acc * ref
+  int64_t dot_ref_pitch;
+  const float* mask;      // fp32 [rows, cols] contiguous, nullable (MASKED): out = acc * mask
+  const uint8_t* tern;    // 2-bit codec bytes of T [rows*cols], nullable (MASKED): partial += acc*T*(1-mask)
+  float* partials;        // [gridDim.x * gridDim.y], nullable
+};
+
+template <int NUM_A, int NUM_B, int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kStageBytes = NUM_A * kABytes + NUM_B * kBBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
+};
+
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    tgemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bars = smem_base + kStages * Cfg::kStageBytes;  // 8-byte aligned
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  const uint32_t tmem_full_bar = bars + 8u * (2 * kStages);
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 1);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 1));
+  float* s_part = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 2));
+
+  const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int64_t n0 = (int64_t)blockIdx.x * BLOCK_N;  // column tile (x fastest: CTAs of one wave share A tiles)
+  const int64_t m0 = (int64_t)blockIdx.y * BLOCK_M;
+  const int num_kb = (int)((p.kdim + BLOCK_K - 1) / BLOCK_K);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (NUM_A == 2) tma_prefetch_desc(&map_a_lo);
+    if (NUM_B == 2) tma_prefetch_desc(&map_b_lo);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 1) {
+    tmem_alloc<BLOCK_N>(tmem_slot);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_gen;
+
+  if (warp_idx == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+        const int32_t kc = kb * BLOCK_K;
+        tma_load_2d(sa, &map_a_hi, kc, (int32_t)m0, full_bar(stage));
+        if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes, &map_a_lo, kc, (int32_t)m0, full_bar(stage));
+        const uint32_t sb = sa + NUM_A * Cfg::kABytes;
+        tma_load_2d(sb, &map_b_hi, kc, (int32_t)n0, full_bar(stage));
+        if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, (int32_t)n0, full_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+        const uint32_t sb = sa + NUM_A * Cfg::kABytes;
+        const uint64_t da_hi = make_smem_desc_kmajor_sw128(sa);
+        const uint64_t da_lo = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
+        const uint64_t db_hi = make_smem_desc_kmajor_sw128(sb);
+        const uint64_t db_lo = make_smem_desc_kmajor_sw128(sb + Cfg::kBBytes);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // 32 B per K step, in 16 B units
+          umma_bf16(tmem_acc, da_hi + koff, db_hi + koff, idesc, accumulate);
+          accumulate = 1;
+          if (NUM_A == 2) umma_bf16(tmem_acc, da_lo + koff, db_hi + koff, idesc, 1u);
+          if (NUM_B == 2) umma_bf16(tmem_acc, da_hi + koff, db_lo + koff, idesc, 1u);
+        }
+        umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above retire
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ================= epilogue warps 2..5 =================
+    const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const int64_t r = m0 + quarter * 32 + lane;
+    const bool row_ok = r < p.rows;
+    const float scale = (EPI == EPI_LINEAR && p.scale != nullptr) ? __ldg(p.scale) : 1.f;
+    float partial = 0.f;
+    const bool vec_out = ((p.out_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0);
+#pragma unroll 1
+    for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+      const int64_t c = n0 + ch * 32;
+      if (c >= p.cols) break;  // warp-uniform
+      uint32_t acc[32];
+      tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), acc);
+      tmem_ld_wait();
+      const bool full_chunk = (c + 32 <= p.cols);
+      if (row_ok) {
+      if constexpr (EPI == EPI_LINEAR) {
+        float* orow = p.out + r * p.out_pitch + c;
+        const float* rrow = p.dot_ref ? p.dot_ref + r * p.dot_ref_pitch + c : nullptr;
+        if (full_chunk && vec_out) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                   __uint_as_float(acc[j + 3]));
+            if (rrow) {
+              partial += v.x * __ldg(rrow + j) + v.y * __ldg(rrow + j + 1) + v.z * __ldg(rrow + j + 2) + v.w * __ldg(rrow + j + 3);
+            }
+            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+            if (p.bias) {
+              v.x += __ldg(p.bias + c + j); v.y += __ldg(p.bias + c + j + 1);
+              v.z += __ldg(p.bias + c + j + 2); v.w += __ldg(p.bias + c + j + 3);
+            }
+            *reinterpret_cast<float4*>(orow + j) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c + j < p.cols) {
+              float v = __uint_as_float(acc[j]);
+              if (rrow) partial += v * __ldg(rrow + j);
+              v *= scale;
+              if (p.bias) v += __ldg(p.bias + c + j);
+              orow[j] = v;
+            }
+          }
+        }
+      } else {
+        float* orow = p.out + r * p.out_pitch + c;
+        const int64_t flat0 = r * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (c + j < p.cols) {
+            const float g = __uint_as_float(acc[j]);
+            const float mk = p.mask ? __ldg(p.mask + flat0 + j) : 1.f;
+            if (p.tern) {
+              const int64_t i = flat0 + j;
+              const uint32_t code = ((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u;
+              partial += g * ((float)code - 1.f) * (1.f - mk);
+            }
+            orow[j] = g * mk;
+          }
+        }
+      }
+      }  // row_ok
+      __syncwarp();  // reconverge before the next warp-aligned tcgen05.ld
+    }
+    if (p.partials != nullptr) {
+      partial = warp_sum(partial);
+      if (lane == 0) s_part[quarter] = partial;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<BLOCK_N>(tmem_acc);
+  }
+  if (p.partials != nullptr && threadIdx.x == 0) {
+    p.partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+  }
+}
+
+// deterministic final sum of the per-CTA partials
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, int64_t n, float* __restrict__ out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) acc += (double)part[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)s[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// bf16 [rows, kdim] row-major with pitch; box = [BLOCK_K, box_rows]; OOB reads return zero
+static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t kdim, int64_t pitch, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return ATQ_ECUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld kdim=%lld pitch=%lld ptr=%p", (int)r, (long long)rows, (long long)kdim,
+              (long long)pitch, (const void*)ptr);
+    return ATQ_ECUDA;
+  }
+  return ATQ_OK;
+}
+
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI>
+static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  int r;
+  if ((r = make_map(&ma_hi, a->hi, p.rows, p.kdim, a->pitch, BLOCK_M)) != ATQ_OK) return r;
+  if ((r = make_map(&mb_hi, b->hi, p.cols, p.kdim, b->pitch, BLOCK_N)) != ATQ_OK) return r;
+  ma_lo = ma_hi;
+  mb_lo = mb_hi;
+  if (NUM_A == 2 && (r = make_map(&ma_lo, a->lo, p.rows, p.kdim, a->pitch, BLOCK_M)) != ATQ_OK) return r;
+  if (NUM_B == 2 && (r = make_map(&mb_lo, b->lo, p.cols, p.kdim, b->pitch, BLOCK_N)) != ATQ_OK) return r;
+  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI>;
+  static bool attr_done_dev[64] = {false};  // per instantiation, per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  bool& attr_done = attr_done_dev[dev & 63];
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+      return ATQ_ECUDA;
+    }
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((p.cols + BLOCK_N - 1) / BLOCK_N), (unsigned)((p.rows + BLOCK_M - 1) / BLOCK_M));
+  if (grid.y > 65535u) {
+    set_error("tgemm: rows too large for one launch (%lld)", (long long)p.rows);
+    return ATQ_EINVAL;
+  }
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("tgemm launch failed: %s", cudaGetErrorString(e));
+    return ATQ_ECUDA;
+  }
+  return ATQ_OK;
+}
+
+template <int EPI>
+static int dispatch(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* bn_used) {
+  const bool a2 = a->lo != nullptr, b2 = b->lo != nullptr;
+  // tile width: 256 columns when the pipeline still has >= 3 stages, else 128; narrow outputs use 64/128
+  const bool narrow = p.cols <= 64;
+  const bool mid = p.cols <= 128;
+#define ATQ_GO(NA, NB, BN) do { *bn_used = BN; return launch_cfg<NA, NB, BN, EPI>(a, b, p, stream); } while (0)
+  if (narrow) {
+    if (a2 && b2) ATQ_GO(2, 2, 64);
+    if (a2) ATQ_GO(2, 1, 64);
+    if (b2) ATQ_GO(1, 2, 64);
+    ATQ_GO(1, 1, 64);
+  }
+  if (a2 && b2) ATQ_GO(2, 2, 128);
+  if (b2) ATQ_GO(1, 2, 128);
+  if (mid) {
+    if (a2) ATQ_GO(2, 1, 128);
+    ATQ_GO(1, 1, 128);
+  }
+  if (a2) ATQ_GO(2, 1, 256);
+  ATQ_GO(1, 1, 256);
+#undef ATQ_GO
+}
+
+static int check_operand(const atq_bf16_operand* o, const char* name) {
+  if (o == nullptr || o->hi == nullptr) {
+    set_error("tgemm: operand %s is null", name);
+    return ATQ_EINVAL;
+  }
+  if ((o->pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(o->hi) & 15u) || (o->lo && (reinterpret_cast<uintptr_t>(o->lo) & 15u))) {
+    set_error("tgemm: operand %s needs pitch %% 8 == 0 and 16-byte aligned pointers", name);
+    return ATQ_EINVAL;
+  }
+  return ATQ_OK;
+}
+
+static int64_t num_tiles_upper(int64_t rows, int64_t cols) {
+  return ((rows + BLOCK_M - 1) / BLOCK_M) * ((cols + 63) / 64);
+}
+
+}  // namespace atq
+
+using namespace atq;
+
+extern "C" {
+
+size_t atq_workspace_bytes_tgemm(int64_t rows, int64_t cols) {
+  return (size_t)(((num_tiles_upper(rows, cols) * sizeof(float)) + 255) & ~(size_t)255);
+}
+
+int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf16_operand* a, const atq_bf16_operand* b,
+              const float* scale, const float* bias, float* out, int64_t out_pitch, const float* dot_ref,
+              int64_t dot_ref_pitch, float* dot_out, void* ws, size_t ws_bytes, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(rows > 0 && cols > 0 && kdim > 0 && out != nullptr && out_pitch >= cols, "bad shape or null output");
+  int r;
+  if ((r = check_operand(a, "a")) != ATQ_OK) return r;
+  if ((r = check_operand(b, "b")) != ATQ_OK) return r;
+  ATQ_CHECK_ARG(a->pitch >= kdim && b->pitch >= kdim, "operand pitch smaller than kdim");
+  ATQ_CHECK_ARG((dot_ref == nullptr) == (dot_out == nullptr), "dot_ref and dot_out go together");
+  if (dot_out != nullptr && (ws == nullptr || ws_bytes < atq_workspace_bytes_tgemm(rows, cols))) {
+    set_error("atq_tgemm: workspace too small");
+    return ATQ_EWORKSPACE;
+  }
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.cols = cols; p.kdim = kdim;
+  p.out = out; p.out_pitch = out_pitch;
+  p.scale = scale; p.bias = bias;
+  p.dot_ref = dot_ref; p.dot_ref_pitch = dot_ref_pitch;
+  p.partials = dot_out ? (float*)ws : nullptr;
+  int bn = 0;
+  if ((r = dispatch<EPI_LINEAR>(a, b, p, stream, &bn)) != ATQ_OK) return r;
+  if (dot_out) {
+    int64_t tiles = ((cols + bn - 1) / bn) * ((rows + BLOCK_M - 1) / BLOCK_M);
+    reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, tiles, dot_out);
+    ATQ_LAUNCH_CHECK();
+  }
+  return ATQ_OK;
+}
+
+int atq_tgemm_fwd(int device, int64_t n_tokens, int64_t out_features, int64_t in_features, const atq_bf16_operand* x,
+                  const atq_bf16_operand* w, const float* alpha, const float* bias, float* y, int64_t y_pitch, void* ws,
+                  size_t ws_bytes, atq_stream_t stream) {
+  return atq_tgemm(device, n_tokens, out_features, in_features, x, w, alpha, bias, y, y_pitch, nullptr, 0, nullptr, ws,
+                   ws_bytes, stream);
+}
+
+int atq_tgemm_dx(int device, int64_t n_tokens, int64_t in_features, int64_t out_features, const atq_bf16_operand* dy,
+                 const atq_bf16_operand* w_t, const float* alpha, float* dx, int64_t dx_pitch, const float* x_ref,
+                 int64_t x_pitch, float* dalpha_out, void* ws, size_t ws_bytes, atq_stream_t stream) {
+  return atq_tgemm(device, n_tokens, in_features, out_features, dy, w_t, alpha, nullptr, dx, dx_pitch, x_ref, x_pitch,
+                   dalpha_out, ws, ws_bytes, stream);
+}
+
+int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, int64_t n_tokens,
+                        const atq_bf16_operand* dy_t, const atq_bf16_operand* x_t, const float* mask,
+                        const uint8_t* packed_t, float* dw, int64_t dw_pitch, float* dalpha_out, void* ws,
+                        size_t ws_bytes, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(out_features > 0 && in_features > 0 && n_tokens > 0 && dw != nullptr && dw_pitch >= in_features,
+                "bad shape or null output");
+  int r;
+  if ((r = check_operand(dy_t, "dy_t")) != ATQ_OK) return r;
+  if ((r = check_operand(x_t, "x_t")) != ATQ_OK) return r;
+  ATQ_CHECK_ARG(dy_t->pitch >= n_tokens && x_t->pitch >= n_tokens, "operand pitch smaller than n_tokens");
+  ATQ_CHECK_ARG((packed_t == nullptr) == (dalpha_out == nullptr), "packed_t and dalpha_out go together");
+  if (dalpha_out != nullptr && (ws == nullptr || ws_bytes < atq_workspace_bytes_tgemm(out_features, in_features))) {
+    set_error("atq_tgemm_dw_masked: workspace too small");
+    return ATQ_EWORKSPACE;
+  }
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = out_features; p.cols = in_features; p.kdim = n_tokens;
+  p.out = dw; p.out_pitch = dw_pitch;
+  p.mask = mask; p.tern = packed_t;
+  p.partials = dalpha_out ? (float*)ws : nullptr;
+  int bn = 0;
+  if ((r = dispatch<EPI_MASKED>(dy_t, x_t, p, stream, &bn)) != ATQ_OK) return r;
+  if (dalpha_out) {
+    int64_t tiles = ((in_features + bn - 1) / bn) * ((out_features + BLOCK_M - 1) / BLOCK_M);
+    reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, tiles, dalpha_out);
+    ATQ_LAUNCH_CHECK();
+  }
+  return ATQ_OK;
+}
+
+}  // extern "C"

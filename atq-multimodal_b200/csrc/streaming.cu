@@ -1,0 +1,693 @@
+// HBM-streaming kernels of the ATQ hot path: |W| statistics, ternarize, 2-bit pack/unpack,
+// routing mask-multiply, bf16 operand builders.  All are coalesced 128-bit load/store,
+// grid-stride kernels sized in multiples of the SM count; integer outputs are bit-exact
+// against the reference (atq/quantizers.py:41-43, atq/bit_packing.py:45-69,104-119).
+#include "common.cuh"
+
+namespace atq {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+struct TernStats {  // 16 bytes
+  unsigned long long nnz;
+  double sum_wt;
+};
+struct AbsStats {  // 16 bytes
+  double sum_abs;
+  unsigned int max_bits;
+  unsigned int pad;
+};
+
+template <bool VEC>
+__device__ __forceinline__ float4 load4(const float* __restrict__ base, int64_t g) {
+  if constexpr (VEC) {
+    return ldg_stream4(base + 4 * g);
+  } else {
+    const float* p = base + 4 * g;
+    return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K1: sum|W| (fp64 accumulate) and max|W|
+// ------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) abs_stats_kernel(const float* __restrict__ w, int64_t n,
+                                                            AbsStats* __restrict__ out) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  float mx = 0.f;
+  for (int64_t g0 = tid; g0 < n4; g0 += stride * kUnroll) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      v[j] = (g < n4) ? load4<VEC>(w, g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      float a0 = fabsf(v[j].x), a1 = fabsf(v[j].y), a2 = fabsf(v[j].z), a3 = fabsf(v[j].w);
+      acc += (double)a0 + (double)a1 + (double)a2 + (double)a3;
+      mx = fmaxf(mx, fmaxf(fmaxf(a0, a1), fmaxf(a2, a3)));
+    }
+  }
+  if (tid == 0) {
+    for (int64_t i = n4 * 4; i < n; ++i) {
+      float a = fabsf(w[i]);
+      acc += (double)a;
+      mx = fmaxf(mx, a);
+    }
+  }
+  __shared__ double s_sum[kThreads / 32];
+  __shared__ float s_max[kThreads / 32];
+  acc = warp_sum(acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    s_sum[wid] = acc;
+    s_max[wid] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    float m = 0.f;
+    for (int i = 0; i < kThreads / 32; ++i) {
+      t += s_sum[i];
+      m = fmaxf(m, s_max[i]);
+    }
+    atomicAdd(&out->sum_abs, t);
+    atomicMax(&out->max_bits, __float_as_uint(m));  // non-negative floats order as uints
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K3 / K4 / K5: ternarize (threshold compare) or validate (already-ternary fp32) -> fp32 T or
+// 2-bit codes.  One float4 (= one packed byte) per thread per step: 512 B loads and 32 B /
+// 512 B stores per warp instruction, all fully coalesced.
+// ------------------------------------------------------------------------------------
+enum { OUT_F32 = 0, OUT_PACK2 = 1 };
+enum { SRC_THRESHOLD = 0, SRC_TERNARY = 1 };
+
+template <int SRC>
+__device__ __forceinline__ uint32_t code_of(float v, float thr, bool& bad) {
+  if constexpr (SRC == SRC_THRESHOLD) {
+    return tern_code(v, thr);
+  } else {
+    // atq/bit_packing.py:36-39,49: only -1, 0 (either sign), +1 are valid
+    uint32_t c = (v == 1.0f) ? 2u : ((v == -1.0f) ? 0u : 1u);
+    bad |= !(v == 1.0f || v == -1.0f || v == 0.0f);
+    return c;
+  }
+}
+
+template <bool VEC, int SRC, int OUT, bool STATS>
+__global__ void __launch_bounds__(kThreads)
+    ternarize_kernel(const float* __restrict__ w, int64_t n, const float* __restrict__ thr_p,
+                     float* __restrict__ t_out, uint8_t* __restrict__ packed, TernStats* __restrict__ stats,
+                     int32_t* __restrict__ invalid_flag) {
+  const float thr = (SRC == SRC_THRESHOLD) ? __ldg(thr_p) : 0.f;
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long nnz = 0;
+  double swt = 0.0;
+  bool bad = false;
+
+  for (int64_t g0 = tid; g0 < n4; g0 += stride * kUnroll) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      if (g < n4) v[j] = load4<VEC>(w, g);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      if (g < n4) {
+        uint32_t c0 = code_of<SRC>(v[j].x, thr, bad), c1 = code_of<SRC>(v[j].y, thr, bad);
+        uint32_t c2 = code_of<SRC>(v[j].z, thr, bad), c3 = code_of<SRC>(v[j].w, thr, bad);
+        if constexpr (STATS) {
+          float t0 = (float)c0 - 1.f, t1 = (float)c1 - 1.f, t2 = (float)c2 - 1.f, t3 = (float)c3 - 1.f;
+          nnz += (c0 != 1u) + (c1 != 1u) + (c2 != 1u) + (c3 != 1u);
+          swt += (double)(v[j].x * t0) + (double)(v[j].y * t1) + (double)(v[j].z * t2) + (double)(v[j].w * t3);
+        }
+        if constexpr (OUT == OUT_PACK2) {
+          packed[g] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+        } else {
+          float4 o = make_float4((float)c0 - 1.f, (float)c1 - 1.f, (float)c2 - 1.f, (float)c3 - 1.f);
+          if constexpr (VEC) {
+            *reinterpret_cast<float4*>(t_out + 4 * g) = o;
+          } else {
+            t_out[4 * g] = o.x; t_out[4 * g + 1] = o.y; t_out[4 * g + 2] = o.z; t_out[4 * g + 3] = o.w;
+          }
+        }
+      }
+    }
+  }
+  if (tid == 0 && (n & 3)) {  // ragged tail: last byte has zero bits above the last code
+    uint32_t byte = 0;
+    for (int64_t i = n4 * 4, j = 0; i < n; ++i, ++j) {
+      float x = w[i];
+      uint32_t c = code_of<SRC>(x, thr, bad);
+      if constexpr (STATS) {
+        nnz += (c != 1u);
+        swt += (double)(x * ((float)c - 1.f));
+      }
+      if constexpr (OUT == OUT_PACK2) byte |= c << (2 * j);
+      else t_out[i] = (float)c - 1.f;
+    }
+    if constexpr (OUT == OUT_PACK2) packed[n4] = (uint8_t)byte;
+  }
+  if constexpr (SRC == SRC_TERNARY) {
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(invalid_flag, 1);
+  }
+  if constexpr (STATS) {
+    __shared__ unsigned long long s_n[kThreads / 32];
+    __shared__ double s_s[kThreads / 32];
+    nnz = warp_sum(nnz);
+    swt = warp_sum(swt);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_n[wid] = nnz; s_s[wid] = swt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long tn = 0; double ts = 0.0;
+      for (int i = 0; i < kThreads / 32; ++i) { tn += s_n[i]; ts += s_s[i]; }
+      atomicAdd(&stats->nnz, tn);
+      atomicAdd(&stats->sum_wt, ts);
+    }
+  }
+}
+
+__global__ void optimal_alpha_kernel(const TernStats* ts, const AbsStats* as, int64_t n, float* alpha_out) {
+  // atq/quantizers.py:49-55 resolved on the device (the reference syncs the host here)
+  if (ts->nnz > 0) {
+    // reference divides an fp32 sum by an fp32 count
+    *alpha_out = (float)ts->sum_wt / (float)ts->nnz;
+  } else {
+    *alpha_out = (float)(as->sum_abs / (double)n);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// K6: unpack 2-bit codes.  One byte -> four values per thread step.
+// ------------------------------------------------------------------------------------
+enum { UNPACK_F32 = 0, UNPACK_BF16 = 1, UNPACK_I8 = 2 };
+
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(kThreads)
+    unpack2_kernel(const uint8_t* __restrict__ packed, int64_t n, void* __restrict__ out_v,
+                   int32_t* __restrict__ invalid_flag) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  for (int64_t g0 = tid; g0 < n4; g0 += stride * kUnroll) {
+    uint32_t b[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      b[j] = (g < n4) ? (uint32_t)__ldg(packed + g) : 0x55u;
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      if (g >= n4) continue;
+      uint32_t c0 = b[j] & 3u, c1 = (b[j] >> 2) & 3u, c2 = (b[j] >> 4) & 3u, c3 = (b[j] >> 6) & 3u;
+      bad |= (c0 == 3u) | (c1 == 3u) | (c2 == 3u) | (c3 == 3u);
+      if constexpr (KIND == UNPACK_F32) {
+        float* out = reinterpret_cast<float*>(out_v);
+        float4 o = make_float4((float)c0 - 1.f, (float)c1 - 1.f, (float)c2 - 1.f, (float)c3 - 1.f);
+        if constexpr (VEC) *reinterpret_cast<float4*>(out + 4 * g) = o;
+        else { out[4 * g] = o.x; out[4 * g + 1] = o.y; out[4 * g + 2] = o.z; out[4 * g + 3] = o.w; }
+      } else if constexpr (KIND == UNPACK_BF16) {
+        uint16_t* out = reinterpret_cast<uint16_t*>(out_v);
+        // bf16: -1 = 0xBF80, 0 = 0, +1 = 0x3F80
+        auto bf = [](uint32_t c) -> uint32_t { return c == 1u ? 0u : (c == 0u ? 0xBF80u : 0x3F80u); };
+        uint2 o = make_uint2(bf(c0) | (bf(c1) << 16), bf(c2) | (bf(c3) << 16));
+        if constexpr (VEC) *reinterpret_cast<uint2*>(out + 4 * g) = o;
+        else { out[4*g] = (uint16_t)bf(c0); out[4*g+1] = (uint16_t)bf(c1); out[4*g+2] = (uint16_t)bf(c2); out[4*g+3] = (uint16_t)bf(c3); }
+      } else {
+        int8_t* out = reinterpret_cast<int8_t*>(out_v);
+        uint32_t o = ((c0 - 1u) & 0xffu) | (((c1 - 1u) & 0xffu) << 8) | (((c2 - 1u) & 0xffu) << 16) | (((c3 - 1u) & 0xffu) << 24);
+        if constexpr (VEC) *reinterpret_cast<uint32_t*>(out + 4 * g) = o;
+        else { out[4*g] = (int8_t)(c0 - 1); out[4*g+1] = (int8_t)(c1 - 1); out[4*g+2] = (int8_t)(c2 - 1); out[4*g+3] = (int8_t)(c3 - 1); }
+      }
+    }
+  }
+  if (tid == 0 && (n & 3)) {
+    uint32_t byte = packed[n4];
+    for (int64_t i = n4 * 4, j = 0; i < n; ++i, ++j) {
+      uint32_t c = (byte >> (2 * j)) & 3u;
+      bad |= (c == 3u);
+      if constexpr (KIND == UNPACK_F32) reinterpret_cast<float*>(out_v)[i] = (float)c - 1.f;
+      else if constexpr (KIND == UNPACK_BF16) reinterpret_cast<uint16_t*>(out_v)[i] = c == 1u ? 0 : (c == 0u ? 0xBF80 : 0x3F80);
+      else reinterpret_cast<int8_t*>(out_v)[i] = (int8_t)((int)c - 1);
+    }
+  }
+  if (invalid_flag != nullptr && __any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicExch(invalid_flag, 1);
+}
+
+// ------------------------------------------------------------------------------------
+// K10: grad_in = grad_out * (|x| > thr)      (atq/routing.py:53-56)
+// ------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads)
+    route_mask_mul_kernel(const float* __restrict__ x, const float* __restrict__ go, const float* __restrict__ thr_p,
+                          int64_t n, float* __restrict__ gi) {
+  const float thr = __ldg(thr_p);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t g0 = tid; g0 < n4; g0 += stride * kUnroll) {
+    float4 a[kUnroll], b[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      if (g < n4) { a[j] = load4<VEC>(x, g); b[j] = load4<VEC>(go, g); }
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      if (g >= n4) continue;
+      // multiply (not select) so that NaN/Inf in grad_out propagate like `grad * mask` does
+      float4 o = make_float4(b[j].x * (fabsf(a[j].x) > thr ? 1.f : 0.f), b[j].y * (fabsf(a[j].y) > thr ? 1.f : 0.f),
+                             b[j].z * (fabsf(a[j].z) > thr ? 1.f : 0.f), b[j].w * (fabsf(a[j].w) > thr ? 1.f : 0.f));
+      if constexpr (VEC) *reinterpret_cast<float4*>(gi + 4 * g) = o;
+      else { gi[4*g] = o.x; gi[4*g+1] = o.y; gi[4*g+2] = o.z; gi[4*g+3] = o.w; }
+    }
+  }
+  if (tid == 0) {
+    for (int64_t i = n4 * 4; i < n; ++i) gi[i] = go[i] * (fabsf(x[i]) > thr ? 1.f : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// fp32 -> bf16 hi/lo split, row-major, for the GEMM A operands
+// ------------------------------------------------------------------------------------
+template <bool HAS_LO>
+__global__ void __launch_bounds__(kThreads)
+    split_flat_kernel(const float* __restrict__ x, int64_t n, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+  // contiguous case (ld_in == cols == pitch): n % 8 == 0 guaranteed by the caller
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t g0 = tid; g0 < n4; g0 += stride * kUnroll) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      if (g < n4) v[j] = ldg_stream4(x + 4 * g);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      int64_t g = g0 + j * stride;
+      if (g >= n4) continue;
+      uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(v[j].x, h0, l0); split_bf16(v[j].y, h1, l1); split_bf16(v[j].z, h2, l2); split_bf16(v[j].w, h3, l3);
+      *reinterpret_cast<uint2*>(hi + 4 * g) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+      if constexpr (HAS_LO)
+        *reinterpret_cast<uint2*>(lo + 4 * g) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+    }
+  }
+}
+
+template <bool HAS_LO>
+__global__ void __launch_bounds__(kThreads)
+    split_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
+                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pitch) {
+  // general strided case: one row per CTA step, scalar coalesced accesses
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* xr = x + r * ld_in;
+    for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+      uint16_t h, l;
+      split_bf16(__ldg(xr + c), h, l);
+      hi[r * pitch + c] = h;
+      if constexpr (HAS_LO) lo[r * pitch + c] = l;
+    }
+  }
+}
+
+// transposed split: x [rows, cols] -> hi_t/lo_t [cols, pitch_t]; 64x64 tiles through shared memory
+constexpr int kTile = 64;
+template <bool HAS_LO>
+__global__ void __launch_bounds__(256)
+    split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
+                   uint16_t* __restrict__ hi_t, uint16_t* __restrict__ lo_t, int64_t pitch_t) {
+  __shared__ float tile[kTile][kTile + 1];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  const int64_t c0 = (int64_t)blockIdx.x * kTile, r0 = (int64_t)blockIdx.y * kTile;
+#pragma unroll 4
+  for (int rr = ty; rr < kTile; rr += 4) {
+    int64_t r = r0 + rr, c = c0 + tx;
+    tile[rr][tx] = (r < rows && c < cols) ? __ldg(x + r * ld_in + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll 4
+  for (int cc = ty; cc < kTile; cc += 4) {
+    int64_t c = c0 + cc, r = r0 + tx;
+    if (c < cols && r < rows) {
+      uint16_t h, l;
+      split_bf16(tile[tx][cc], h, l);
+      hi_t[c * pitch_t + r] = h;
+      if constexpr (HAS_LO) lo_t[c * pitch_t + r] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Quantize-and-build: one pass over W [M,K] producing the 2-bit codec bytes and the bf16
+// GEMM operands in both orientations.  MIXED adds the RPB formula
+// Wm = T*alpha*(1-mask) + W*mask  (atq/precision_boost.py:72).
+// ------------------------------------------------------------------------------------
+template <bool MIXED>
+__global__ void __launch_bounds__(256)
+    build_operands_kernel(const float* __restrict__ w, const float* __restrict__ mask, int64_t M, int64_t K,
+                          const float* __restrict__ thr_p, const float* __restrict__ alpha_p,
+                          uint8_t* __restrict__ packed,
+                          uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pitch,
+                          uint16_t* __restrict__ hi_t, uint16_t* __restrict__ lo_t, int64_t pitch_t,
+                          TernStats* __restrict__ stats) {
+  __shared__ float tile[kTile][kTile + 1];      // value that goes to the bf16 operands
+  __shared__ uint8_t codes[kTile][kTile + 4];   // 2-bit codes of T (for the codec bytes)
+  const float thr = __ldg(thr_p);
+  const float alpha = MIXED ? __ldg(alpha_p) : 1.f;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int64_t k0 = (int64_t)blockIdx.x * kTile, m0 = (int64_t)blockIdx.y * kTile;
+  unsigned long long nnz = 0;
+  double swt = 0.0;
+#pragma unroll 4
+  for (int rr = ty; rr < kTile; rr += 4) {
+    int64_t m = m0 + rr, k = k0 + tx;
+    float val = 0.f;
+    uint32_t c = 1u;
+    if (m < M && k < K) {
+      float x = __ldg(w + m * K + k);
+      c = tern_code(x, thr);
+      float t = (float)c - 1.f;
+      if constexpr (MIXED) {
+        float mk = __ldg(mask + m * K + k);
+        // same expression order as the reference: ((T*alpha)*(1-mask)) + (W*mask), fp32
+        val = (t * alpha) * (1.f - mk) + x * mk;
+      } else {
+        val = t;
+        nnz += (c != 1u);
+        swt += (double)(x * t);
+      }
+      if (hi != nullptr) {
+        uint16_t h, l;
+        split_bf16(val, h, l);
+        hi[m * pitch + k] = h;
+        if (MIXED && lo != nullptr) lo[m * pitch + k] = l;
+      }
+    }
+    tile[rr][tx] = val;
+    codes[rr][tx] = (uint8_t)c;
+  }
+  __syncthreads();
+  if (packed != nullptr) {  // K % 4 == 0 (checked by the host): 16 bytes per tile row
+    for (int i = threadIdx.x; i < kTile * (kTile / 4); i += 256) {
+      int rr = i >> 4, bj = i & 15;
+      int64_t m = m0 + rr, k = k0 + 4 * bj;
+      if (m < M && k < K) {
+        uint32_t b = codes[rr][4 * bj] | (codes[rr][4 * bj + 1] << 2) | (codes[rr][4 * bj + 2] << 4) | (codes[rr][4 * bj + 3] << 6);
+        // columns beyond K inside this byte cannot occur because K % 4 == 0
+        packed[(m * K + k) >> 2] = (uint8_t)b;
+      }
+    }
+  }
+  if (hi_t != nullptr) {
+#pragma unroll 4
+    for (int cc = ty; cc < kTile; cc += 4) {
+      int64_t k = k0 + cc, m = m0 + tx;
+      if (k < K && m < M) {
+        uint16_t h, l;
+        split_bf16(tile[tx][cc], h, l);
+        hi_t[k * pitch_t + m] = h;
+        if (MIXED && lo_t != nullptr) lo_t[k * pitch_t + m] = l;
+      }
+    }
+  }
+  if constexpr (!MIXED) {
+    if (stats != nullptr) {
+      __shared__ unsigned long long s_n[8];
+      __shared__ double s_s[8];
+      nnz = warp_sum(nnz);
+      swt = warp_sum(swt);
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+      if (lane == 0) { s_n[wid] = nnz; s_s[wid] = swt; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long tn = 0; double ts = 0.0;
+        for (int i = 0; i < 8; ++i) { tn += s_n[i]; ts += s_s[i]; }
+        atomicAdd(&stats->nnz, tn);
+        atomicAdd(&stats->sum_wt, ts);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// column sums (bias gradient): deterministic two-stage reduction
+// ------------------------------------------------------------------------------------
+constexpr int kColsumRowsPerCta = 256;
+__global__ void __launch_bounds__(256)
+    colsum_stage1_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ part) {
+  // CTA = 32 columns x kColsumRowsPerCta rows; 8 warps take interleaved rows
+  __shared__ float s[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.y * kColsumRowsPerCta;
+  const int64_t r1 = min(rows, r0 + kColsumRowsPerCta);
+  float acc = 0.f;
+  if (c < cols)
+    for (int64_t r = r0 + wid; r < r1; r += 8) acc += __ldg(x + r * ld + c);
+  s[wid][lane] = acc;
+  __syncthreads();
+  if (wid == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][lane];
+    part[(int64_t)blockIdx.y * cols + c] = t;
+  }
+}
+__global__ void __launch_bounds__(256)
+    colsum_stage2_kernel(const float* __restrict__ part, int64_t nparts, int64_t cols, float* __restrict__ out) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int64_t p = 0; p < nparts; ++p) t += part[p * cols + c];
+  out[c] = t;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace atq
+
+using namespace atq;
+
+template <int KIND>
+static int launch_unpack(int device, const uint8_t* packed, int64_t n, void* out, int32_t* flag, cudaStream_t stream) {
+  int grid = stream_grid(device, (n >> 2) + 1, kThreads * kUnroll, 8);
+  if (aligned16(out)) unpack2_kernel<KIND, true><<<grid, kThreads, 0, stream>>>(packed, n, out, flag);
+  else unpack2_kernel<KIND, false><<<grid, kThreads, 0, stream>>>(packed, n, out, flag);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+extern "C" {
+
+size_t atq_workspace_bytes_abs_stats(int64_t) { return 0; }
+
+int atq_abs_stats(int device, const float* w, int64_t n, void* stats_out, void*, size_t, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(w != nullptr && stats_out != nullptr && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ATQ_CUDA(cudaMemsetAsync(stats_out, 0, sizeof(AbsStats), stream));
+  int grid = stream_grid(device, (n >> 2) + 1, kThreads * kUnroll, 8);
+  if (aligned16(w)) abs_stats_kernel<true><<<grid, kThreads, 0, stream>>>(w, n, (AbsStats*)stats_out);
+  else abs_stats_kernel<false><<<grid, kThreads, 0, stream>>>(w, n, (AbsStats*)stats_out);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+static int launch_ternarize(int device, const float* w, int64_t n, const float* thr, float* t_out, uint8_t* packed,
+                            void* stats, cudaStream_t stream) {
+  int grid = stream_grid(device, (n >> 2) + 1, kThreads * kUnroll, 8);
+  const bool vec = aligned16(w) && (t_out == nullptr || aligned16(t_out));
+  TernStats* st = (TernStats*)stats;
+#define ATQ_TERN(V, O, S) ternarize_kernel<V, SRC_THRESHOLD, O, S><<<grid, kThreads, 0, stream>>>(w, n, thr, t_out, packed, st, nullptr)
+  if (t_out != nullptr) {
+    if (vec) { if (st) ATQ_TERN(true, OUT_F32, true); else ATQ_TERN(true, OUT_F32, false); }
+    else     { if (st) ATQ_TERN(false, OUT_F32, true); else ATQ_TERN(false, OUT_F32, false); }
+  } else {
+    if (vec) { if (st) ATQ_TERN(true, OUT_PACK2, true); else ATQ_TERN(true, OUT_PACK2, false); }
+    else     { if (st) ATQ_TERN(false, OUT_PACK2, true); else ATQ_TERN(false, OUT_PACK2, false); }
+  }
+#undef ATQ_TERN
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_ternarize_f32(int device, const float* w, int64_t n, const float* thr, float* t_out, void* stats,
+                      atq_stream_t stream) {
+  ATQ_CHECK_ARG(w && thr && t_out && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return launch_ternarize(device, w, n, thr, t_out, nullptr, stats, (cudaStream_t)stream);
+}
+
+int atq_ternarize_pack2(int device, const float* w, int64_t n, const float* thr, uint8_t* packed, void* stats,
+                        atq_stream_t stream) {
+  ATQ_CHECK_ARG(w && thr && packed && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return launch_ternarize(device, w, n, thr, nullptr, packed, stats, (cudaStream_t)stream);
+}
+
+int atq_optimal_alpha(int device, const void* tern_stats, const void* abs_stats, int64_t n, float* alpha_out,
+                      atq_stream_t stream) {
+  ATQ_CHECK_ARG(tern_stats && abs_stats && alpha_out && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  optimal_alpha_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const TernStats*)tern_stats, (const AbsStats*)abs_stats, n, alpha_out);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_pack2_from_f32(int device, const float* t, int64_t n, uint8_t* packed, int32_t* invalid_flag,
+                       atq_stream_t stream_) {
+  ATQ_CHECK_ARG(t && packed && invalid_flag && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int grid = stream_grid(device, (n >> 2) + 1, kThreads * kUnroll, 8);
+  if (aligned16(t))
+    ternarize_kernel<true, SRC_TERNARY, OUT_PACK2, false><<<grid, kThreads, 0, stream>>>(t, n, nullptr, nullptr, packed, nullptr, invalid_flag);
+  else
+    ternarize_kernel<false, SRC_TERNARY, OUT_PACK2, false><<<grid, kThreads, 0, stream>>>(t, n, nullptr, nullptr, packed, nullptr, invalid_flag);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_unpack2_to_f32(int device, const uint8_t* packed, int64_t n, float* out, int32_t* invalid_flag, atq_stream_t stream) {
+  ATQ_CHECK_ARG(packed && out && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return launch_unpack<UNPACK_F32>(device, packed, n, out, invalid_flag, (cudaStream_t)stream);
+}
+int atq_unpack2_to_bf16(int device, const uint8_t* packed, int64_t n, uint16_t* out, atq_stream_t stream) {
+  ATQ_CHECK_ARG(packed && out && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return launch_unpack<UNPACK_BF16>(device, packed, n, out, nullptr, (cudaStream_t)stream);
+}
+int atq_unpack2_to_i8(int device, const uint8_t* packed, int64_t n, int8_t* out, atq_stream_t stream) {
+  ATQ_CHECK_ARG(packed && out && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return launch_unpack<UNPACK_I8>(device, packed, n, out, nullptr, (cudaStream_t)stream);
+}
+
+int atq_route_mask_mul(int device, const float* x, const float* grad_out, const float* thr, int64_t n, float* grad_in,
+                       atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && grad_out && thr && grad_in && n > 0, "null pointer or n <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int grid = stream_grid(device, (n >> 2) + 1, kThreads * kUnroll, 8);
+  if (aligned16(x) && aligned16(grad_out) && aligned16(grad_in))
+    route_mask_mul_kernel<true><<<grid, kThreads, 0, stream>>>(x, grad_out, thr, n, grad_in);
+  else
+    route_mask_mul_kernel<false><<<grid, kThreads, 0, stream>>>(x, grad_out, thr, n, grad_in);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_split_bf16(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in, uint16_t* hi, uint16_t* lo,
+                   int64_t pitch, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && hi && rows > 0 && cols > 0, "null pointer or empty shape");
+  ATQ_CHECK_ARG(ld_in >= cols && pitch >= cols && (pitch % 8) == 0, "need ld_in >= cols, pitch >= cols, pitch % 8 == 0");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (ld_in == cols && pitch == cols && aligned16(x) && aligned16(hi) && (lo == nullptr || aligned16(lo))) {
+    int64_t n = rows * cols;
+    int grid = stream_grid(device, n >> 2, kThreads * kUnroll, 8);
+    if (lo) split_flat_kernel<true><<<grid, kThreads, 0, stream>>>(x, n, hi, lo);
+    else split_flat_kernel<false><<<grid, kThreads, 0, stream>>>(x, n, hi, lo);
+  } else {
+    int grid = (int)(rows < (int64_t)sm_count(device) * 8 ? rows : (int64_t)sm_count(device) * 8);
+    if (lo) split_rows_kernel<true><<<grid, kThreads, 0, stream>>>(x, rows, cols, ld_in, hi, lo, pitch);
+    else split_rows_kernel<false><<<grid, kThreads, 0, stream>>>(x, rows, cols, ld_in, hi, lo, pitch);
+  }
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in, uint16_t* hi_t,
+                     uint16_t* lo_t, int64_t pitch_t, float* colsum, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && hi_t && rows > 0 && cols > 0, "null pointer or empty shape");
+  ATQ_CHECK_ARG(ld_in >= cols && pitch_t >= rows && (pitch_t % 8) == 0, "need ld_in >= cols, pitch_t >= rows, pitch_t % 8 == 0");
+  ATQ_CHECK_ARG(colsum == nullptr, "fused colsum not supported in this build; use atq_colsum_f32");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  dim3 grid((unsigned)((cols + kTile - 1) / kTile), (unsigned)((rows + kTile - 1) / kTile));
+  ATQ_CHECK_ARG(grid.y <= 65535u, "rows too large for one launch");
+  if (lo_t) split_t_kernel<true><<<grid, 256, 0, stream>>>(x, rows, cols, ld_in, hi_t, lo_t, pitch_t);
+  else split_t_kernel<false><<<grid, 256, 0, stream>>>(x, rows, cols, ld_in, hi_t, lo_t, pitch_t);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_build_ternary_operands(int device, const float* w, int64_t M, int64_t K, const float* thr, uint8_t* packed,
+                               uint16_t* tb, int64_t pitch, uint16_t* tb_t, int64_t pitch_t, void* stats,
+                               atq_stream_t stream_) {
+  ATQ_CHECK_ARG(w && thr && M > 0 && K > 0, "null pointer or empty shape");
+  ATQ_CHECK_ARG(packed == nullptr || (K % 4) == 0, "packed output needs K % 4 == 0 (use atq_ternarize_pack2)");
+  ATQ_CHECK_ARG(tb == nullptr || (pitch >= K && pitch % 8 == 0), "bad pitch");
+  ATQ_CHECK_ARG(tb_t == nullptr || (pitch_t >= M && pitch_t % 8 == 0), "bad pitch_t");
+  ATQ_ENSURE_DEVICE(device);
+  dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((M + kTile - 1) / kTile));
+  ATQ_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
+  build_operands_kernel<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, nullptr, M, K, thr, nullptr, packed, tb, nullptr, pitch,
+                                                                         tb_t, nullptr, pitch_t, (TernStats*)stats);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_build_mixed_operands(int device, const float* w, const float* mask, int64_t M, int64_t K, const float* thr,
+                             const float* alpha, uint8_t* packed, uint16_t* hi, uint16_t* lo, int64_t pitch,
+                             uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(w && mask && thr && alpha && M > 0 && K > 0, "null pointer or empty shape");
+  ATQ_CHECK_ARG(packed == nullptr || (K % 4) == 0, "packed output needs K % 4 == 0 (use atq_ternarize_pack2)");
+  ATQ_CHECK_ARG(hi == nullptr || (pitch >= K && pitch % 8 == 0), "bad pitch");
+  ATQ_CHECK_ARG(hi_t == nullptr || (pitch_t >= M && pitch_t % 8 == 0), "bad pitch_t");
+  ATQ_ENSURE_DEVICE(device);
+  dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((M + kTile - 1) / kTile));
+  ATQ_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
+  build_operands_kernel<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, mask, M, K, thr, alpha, packed, hi, lo, pitch, hi_t, lo_t,
+                                                                        pitch_t, nullptr);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+size_t atq_workspace_bytes_colsum(int64_t rows, int64_t cols) {
+  int64_t parts = (rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta;
+  return (size_t)(parts * cols * sizeof(float));
+}
+
+int atq_colsum_f32(int device, const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* ws,
+                   size_t ws_bytes, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && out && rows > 0 && cols > 0 && ld >= cols, "null pointer or bad shape");
+  ATQ_ENSURE_DEVICE(device);
+  if (ws_bytes < atq_workspace_bytes_colsum(rows, cols) || ws == nullptr) {
+    set_error("atq_colsum_f32: workspace too small");
+    return ATQ_EWORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int64_t parts = (rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta;
+  dim3 g1((unsigned)((cols + 31) / 32), (unsigned)parts);
+  ATQ_CHECK_ARG(parts <= 65535, "rows too large for one launch");
+  colsum_stage1_kernel<<<g1, 256, 0, stream>>>(x, rows, cols, ld, (float*)ws);
+  ATQ_LAUNCH_CHECK();
+  colsum_stage2_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>((const float*)ws, parts, cols, out);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+/*
+ * atq_sm100.h -- C ABI of libatq_sm100.so, the B200 (sm_100a) implementation of the ATQ
+ * ternary hot path.  This is the drop-in boundary: plain pointers and sizes, no torch types.
+ *
+ * The reference (ak736/ATQ-Multimodal) has no FFI layer; its hot path is Python over ATen
+ * (SURVEY.md 8b).  Each entry point below names the reference lines whose work it replaces
+ * (paths relative to the reference root).  The Python package atq-multimodal_b200/atq binds
+ * these with ctypes (atq/_native.py) and keeps the reference's module signatures.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer on `device` unless the name ends in _host.
+ *  - Every compute call is asynchronous on `stream` (a cudaStream_t / CUstream handle;
+ *    0 = legacy default stream), never synchronises, never allocates or frees, and never
+ *    retains a pointer after the work it enqueued completes.
+ *  - Scratch memory is provided by the caller: `ws` must hold at least
+ *    atq_workspace_bytes_<op>(...) bytes, 256-byte aligned, and stay alive until the stream
+ *    work completes.  Calls on one stream may share one workspace.
+ *  - Return value: ATQ_OK or a negative atq_status; atq_last_error_string() (thread-local)
+ *    describes the last failure.
+ *  - Scalars that the reference keeps as 0-dim tensors (threshold, alpha) stay on the
+ *    device: no entry point reads them back to the host.
+ */
+#ifndef ATQ_SM100_H
+#define ATQ_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ATQ_OK = 0,
+  ATQ_EINVAL = -1,     /* bad shape / alignment / null pointer            */
+  ATQ_EARCH = -2,      /* device is not compute capability 10.x           */
+  ATQ_ECUDA = -3,      /* a CUDA runtime/driver call failed               */
+  ATQ_EWORKSPACE = -4  /* workspace too small                             */
+} atq_status;
+
+typedef void* atq_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------- */
+int atq_abi_version(void);                 /* bumps on any signature change */
+const char* atq_last_error_string(void);
+int atq_device_check(int device);          /* ATQ_OK iff `device` is sm_100-class */
+int atq_num_sms(int device);
+
+/* ---- A1: per-layer adaptive threshold  (atq/quantizers.py:21-38) -------------------- */
+/* K1: grid-level |W| reduction.  stats_out (device, 16 bytes): double sum|W|; float max|W|; u32 pad. */
+size_t atq_workspace_bytes_abs_stats(int64_t n);
+int atq_abs_stats(int device, const float* w, int64_t n, void* stats_out,
+                  void* ws, size_t ws_bytes, atq_stream_t stream);
+
+/* K2: exact k-th smallest |x| (0-indexed, ascending), i.e. torch.sort(|x|).values[k]
+ * (atq/quantizers.py:25-32) and torch.kthvalue(|x|, k+1) (atq/routing.py:48).
+ * Bit-exact: the result is an element of |x|.  0 <= k < n. */
+size_t atq_workspace_bytes_select_kth_abs(int64_t n);
+int atq_select_kth_abs(int device, const float* x, int64_t n, int64_t k, float* thr_out,
+                       void* ws, size_t ws_bytes, atq_stream_t stream);
+
+/* The whole threshold stage with the reference's three branches, keyed by
+ * k = int(sparsity_target * n) computed by the caller in double precision:
+ *   0 < k < n : k-th order statistic           (:31-32)
+ *   k >= n    : max|W| + 1.0                   (:33-35)
+ *   k <= 0    : threshold_factor * mean|W|     (:36-38)   */
+size_t atq_workspace_bytes_adaptive_threshold(int64_t n);
+int atq_adaptive_threshold(int device, const float* w, int64_t n, int64_t k, float threshold_factor,
+                           float* thr_out, void* ws, size_t ws_bytes, atq_stream_t stream);
+
+/* Batched form: `count` independent layers in one launch sequence (one threshold each).
+ * w_ptrs_host/n_host/k_host/thr_ptrs_host are HOST arrays of length count. */
+size_t atq_workspace_bytes_adaptive_threshold_batched(int count, const int64_t* n_host);
+int atq_adaptive_threshold_batched(int device, int count, const float* const* w_ptrs_host,
+                                   const int64_t* n_host, const int64_t* k_host, float threshold_factor,
+                                   float* const* thr_ptrs_host, void* ws, size_t ws_bytes,
+                                   atq_stream_t stream);
+
+/* ---- A2/A3: ternarize (+ optional optimal-alpha statistics) (atq/quantizers.py:41-59) -- */
+/* stats (nullable, device, 16 bytes, accumulated into -- caller zeroes): u64 nnz; double sum(W*T). */
+int atq_ternarize_f32(int device, const float* w, int64_t n, const float* thr, float* t_out,
+                      void* stats, atq_stream_t stream);
+/* K4: fused ternarize -> 2-bit pack in the reference's codec layout (atq/bit_packing.py:45-69). */
+int atq_ternarize_pack2(int device, const float* w, int64_t n, const float* thr, uint8_t* packed,
+                        void* stats, atq_stream_t stream);
+/* alpha* = sum(W*T)/nnz, or mean|W| when nnz == 0 (:49-55), resolved on the device.
+ * tern_stats as above; abs_stats as written by atq_abs_stats. */
+int atq_optimal_alpha(int device, const void* tern_stats, const void* abs_stats, int64_t n,
+                      float* alpha_out, atq_stream_t stream);
+
+/* ---- E1/E2: 2-bit codec (atq/bit_packing.py:22-119) --------------------------------- */
+/* code = value+1, element i at bits 2(i%4).. of byte i/4, tail bits zero.
+ * invalid_flag (device int32, caller zeroes): set to 1 if any input is not in {-1,0,+1}
+ * (reference raises ValueError at :39) / if any 2-bit code is 3 (reference KeyError at :116). */
+int atq_pack2_from_f32(int device, const float* t, int64_t n, uint8_t* packed, int32_t* invalid_flag,
+                       atq_stream_t stream);
+int atq_unpack2_to_f32(int device, const uint8_t* packed, int64_t n, float* out, int32_t* invalid_flag,
+                       atq_stream_t stream);
+int atq_unpack2_to_bf16(int device, const uint8_t* packed, int64_t n, uint16_t* out, atq_stream_t stream);
+int atq_unpack2_to_i8(int device, const uint8_t* packed, int64_t n, int8_t* out, atq_stream_t stream);
+
+/* ---- D2: selective gradient routing backward (atq/routing.py:53-56) ------------------ */
+/* grad_in = grad_out * (|x| > *thr) */
+int atq_route_mask_mul(int device, const float* x, const float* grad_out, const float* thr, int64_t n,
+                       float* grad_in, atq_stream_t stream);
+
+/* ---- GEMM operand builders ----------------------------------------------------------- */
+/* fp32 [rows, cols] (row pitch ld_in elements) -> bf16 hi (+ lo = bf16(x - hi), nullable)
+ * [rows, pitch]; pitch % 8 == 0, pitch >= cols; padding columns are left untouched. */
+int atq_split_bf16(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in,
+                   uint16_t* hi, uint16_t* lo, int64_t pitch, atq_stream_t stream);
+/* same, transposed output: hi_t/lo_t are [cols, pitch_t], pitch_t % 8 == 0, pitch_t >= rows.
+ * colsum is reserved (must be NULL; use atq_colsum_f32). */
+int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in,
+                     uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, float* colsum, atq_stream_t stream);
+
+/* Quantize a layer into everything its GEMMs consume, in one pass over W [M,K]:
+ *  packed   : 2-bit codec bytes of T (public format, flat row-major), nullable
+ *  tb       : T as bf16 [M, pitch]  (forward B operand), nullable
+ *  tb_t     : T^T as bf16 [K, pitch_t] (dX B operand), nullable
+ * replaces atq/quantizers.py:41-43 + the `w_ternary * alpha` materialisation of atq/layers.py:43. */
+int atq_build_ternary_operands(int device, const float* w, int64_t M, int64_t K, const float* thr,
+                               uint8_t* packed, uint16_t* tb, int64_t pitch, uint16_t* tb_t, int64_t pitch_t,
+                               void* stats, atq_stream_t stream);
+/* Residual-precision-boost mixed weight (atq/precision_boost.py:72):
+ *  Wm = T*alpha*(1-mask) + W*mask, emitted as bf16 hi/lo pairs [M,pitch] and transposed
+ *  [K,pitch_t]; lo pointers nullable (fast mode).  packed as above (nullable). */
+int atq_build_mixed_operands(int device, const float* w, const float* mask, int64_t M, int64_t K,
+                             const float* thr, const float* alpha, uint8_t* packed,
+                             uint16_t* hi, uint16_t* lo, int64_t pitch,
+                             uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, atq_stream_t stream);
+
+/* ---- ternary GEMMs (tcgen05 / TMEM / TMA) -------------------------------------------- */
+/* Common operand description: a bf16 matrix [rows, kdim] with row pitch `pitch` elements
+ * (pitch % 8 == 0, base 16-byte aligned), given as hi (+ optional lo) so that the fp32
+ * value is hi + lo.  */
+typedef struct {
+  const uint16_t* hi;
+  const uint16_t* lo; /* nullable */
+  int64_t pitch;
+} atq_bf16_operand;
+
+/* K7 forward:  Y[N,M] = scale * (X[N,K] . B[M,K]^T) + bias      (atq/layers.py:43,
+ * atq/precision_boost.py:74, atq/bit_packing.py:165-176).
+ *  - TernaryLinear: B = T (tb, exact in bf16), scale = alpha (device scalar).
+ *  - RPB: B = Wm hi/lo, scale = NULL.
+ * K8 dX:  dX[N,K] = scale * (dY[N,M] . Bt[K,M]^T); with dot_ref = X it also returns
+ *  dot_out = sum(acc .* X) = d(alpha) of TernaryLinear (autograd's sum(G.*T)).
+ * Both are this one entry point: D[rows,cols] = scale*(A . B^T) (+bias[cols]).           */
+size_t atq_workspace_bytes_tgemm(int64_t rows, int64_t cols);
+int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim,
+              const atq_bf16_operand* a, const atq_bf16_operand* b,
+              const float* scale, const float* bias,
+              float* out, int64_t out_pitch,
+              const float* dot_ref, int64_t dot_ref_pitch, float* dot_out,
+              void* ws, size_t ws_bytes, atq_stream_t stream);
+/* named wrappers (same arguments), kept for readability at the call sites */
+int atq_tgemm_fwd(int device, int64_t n_tokens, int64_t out_features, int64_t in_features,
+                  const atq_bf16_operand* x, const atq_bf16_operand* w,
+                  const float* alpha, const float* bias, float* y, int64_t y_pitch,
+                  void* ws, size_t ws_bytes, atq_stream_t stream);
+int atq_tgemm_dx(int device, int64_t n_tokens, int64_t in_features, int64_t out_features,
+                 const atq_bf16_operand* dy, const atq_bf16_operand* w_t,
+                 const float* alpha, float* dx, int64_t dx_pitch,
+                 const float* x_ref, int64_t x_pitch, float* dalpha_out,
+                 void* ws, size_t ws_bytes, atq_stream_t stream);
+/* K9 masked dW:  G[M,K] = dY^T[M,N] . X^T[K,N]^T;  dW = G .* mask (mask NULL = STE opt-in: dW = G);
+ * dalpha_out (nullable) = sum(G .* T .* (1-mask)), T read from the 2-bit codec bytes
+ * (autograd of atq/precision_boost.py:72). */
+int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, int64_t n_tokens,
+                        const atq_bf16_operand* dy_t, const atq_bf16_operand* x_t,
+                        const float* mask, const uint8_t* packed_t,
+                        float* dw, int64_t dw_pitch, float* dalpha_out,
+                        void* ws, size_t ws_bytes, atq_stream_t stream);
+
+/* fp32 helpers used by the layer wrappers: out[i] (+)= ... tiny device-side reductions */
+/* out[c] = sum_r x[r,c]  (bias gradient); deterministic two-stage reduction */
+size_t atq_workspace_bytes_colsum(int64_t rows, int64_t cols);
+int atq_colsum_f32(int device, const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
+                   void* ws, size_t ws_bytes, atq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATQ_SM100_H */
