@@ -1,0 +1,425 @@
+"""Synthetic-workload callers of the ATQ hot path (bench / test harness, NOT part of the product).
+
+The reference's models/ package does not travel to the GPU box, so the benchmark needs its
+own callers.  These modules re-create, from the structure documented in SURVEY.md 3.2-3.3, the
+networks the reference's two scripts train -- same layer shapes, same op order, same
+parameter/buffer names (so a reference state_dict loads with strict=False; only `fusion.*`,
+which never executes on the training path, is absent) -- with the ternary layer classes
+injected: `layers` is any namespace providing TernaryLinear / ResidualPrecisionBoostLinear
+(the B200 `atq` package on the GPU arm, the CPU oracle modules on the reference arm).
+
+tests/test_workloads.py checks them against the reference's own models in the build container.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _lengths_to_mask(lengths, batch, seq, device):
+    # True = padding (models/text_encoder.py:389-396)
+    return torch.arange(seq, device=device).expand(batch, seq) >= lengths.to(device).unsqueeze(1)
+
+
+class TernaryAttention(nn.Module):
+    """models/text_encoder.py:10-163 (TernaryMultiheadAttention, critical_attention=True)."""
+
+    def __init__(self, layers, embed_dim, num_heads, dropout, use_rpb, sparsity_target):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim
+        self.initial_sparsity = min(0.1, sparsity_target)
+        self.target_sparsity = sparsity_target
+        s0 = self.initial_sparsity
+        if use_rpb:
+            self.q_proj = layers.ResidualPrecisionBoostLinear(embed_dim, embed_dim, precision_ratio=0.2, sparsity_target=s0)
+            self.k_proj = layers.ResidualPrecisionBoostLinear(embed_dim, embed_dim, precision_ratio=0.2, sparsity_target=s0)
+            self.v_proj = layers.ResidualPrecisionBoostLinear(embed_dim, embed_dim, precision_ratio=0.2, sparsity_target=s0)
+            self.out_proj = layers.ResidualPrecisionBoostLinear(embed_dim, embed_dim, precision_ratio=0.4, sparsity_target=s0)
+        else:
+            self.q_proj = layers.TernaryLinear(embed_dim, embed_dim)
+            self.k_proj = layers.TernaryLinear(embed_dim, embed_dim)
+            self.v_proj = layers.TernaryLinear(embed_dim, embed_dim)
+            self.out_proj = layers.TernaryLinear(embed_dim, embed_dim)
+        self.attention_scale = 1.0 / math.sqrt(self.head_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.pre_layer_norm = nn.LayerNorm(embed_dim)
+
+    def update_sparsity(self, progress):
+        s = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
+        for m in (self.q_proj, self.k_proj, self.v_proj, self.out_proj):
+            if hasattr(m, "sparsity_target"):
+                m.sparsity_target = s
+
+    def forward(self, query, key, value, key_padding_mask=None):
+        query = self.pre_layer_norm(query)
+        b = query.size(0)
+        q, k, v = self.q_proj(query), self.k_proj(key), self.v_proj(value)
+        q = q.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
+        k = k.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
+        v = v.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
+        scores = torch.matmul(q, k.transpose(-2, -1)) * self.attention_scale
+        if key_padding_mask is not None:
+            scores = scores.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+        probs = self.dropout(F.softmax(scores, dim=-1))
+        out = torch.matmul(probs, v).transpose(1, 2).contiguous().view(b, -1, self.embed_dim)
+        return self.out_proj(out) + 0.1 * query
+
+
+class TernaryBlock(nn.Module):
+    """models/text_encoder.py:166-249 (TernaryTransformerLayer): pre-norm, gated residuals."""
+
+    def __init__(self, layers, embed_dim, num_heads, dim_feedforward, dropout, use_rpb, sparsity_target):
+        super().__init__()
+        self.initial_sparsity = min(0.1, sparsity_target)
+        self.target_sparsity = sparsity_target
+        s0 = self.initial_sparsity
+        self.self_attn = TernaryAttention(layers, embed_dim, num_heads, dropout, use_rpb, s0)
+        if use_rpb:
+            self.linear1 = layers.ResidualPrecisionBoostLinear(embed_dim, dim_feedforward, precision_ratio=0.2, sparsity_target=s0)
+            self.linear2 = layers.ResidualPrecisionBoostLinear(dim_feedforward, embed_dim, precision_ratio=0.4, sparsity_target=s0)
+        else:
+            self.linear1 = layers.TernaryLinear(embed_dim, dim_feedforward)
+            self.linear2 = layers.TernaryLinear(dim_feedforward, embed_dim)
+        self.norm1 = nn.LayerNorm(embed_dim)
+        self.norm2 = nn.LayerNorm(embed_dim)
+        self.dropout = nn.Dropout(dropout)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.gate = nn.Parameter(torch.ones(1) * 0.8)
+
+    def update_sparsity(self, progress):
+        s = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
+        self.self_attn.update_sparsity(progress)
+        for m in (self.linear1, self.linear2):
+            if hasattr(m, "sparsity_target"):
+                m.sparsity_target = s
+
+    def forward(self, src, key_padding_mask=None):
+        h = self.norm1(src)
+        h = self.self_attn(h, h, h, key_padding_mask=key_padding_mask)
+        gate = torch.sigmoid(self.gate)
+        src = src + self.dropout1(h) * gate
+        h = self.norm2(src)
+        h = self.linear2(self.dropout(F.gelu(self.linear1(h))))
+        return src + self.dropout2(h) * gate
+
+
+class TextEncoder(nn.Module):
+    """models/text_encoder.py:252-433 (ATQTextEncoder)."""
+
+    def __init__(self, layers, vocab_size, embed_dim=128, num_heads=8, num_layers=4, dim_feedforward=512,
+                 dropout=0.1, use_rpb=True, sparsity_target=0.3, max_seq_length=256):
+        super().__init__()
+        self.embed_dim, self.use_rpb = embed_dim, use_rpb
+        self.initial_sparsity = min(0.1, sparsity_target)
+        self.target_sparsity = sparsity_target
+        s0 = self.initial_sparsity
+        self.embedding = nn.Embedding(vocab_size, embed_dim)
+        self.embed_norm = nn.LayerNorm(embed_dim)
+        pe = torch.zeros(max_seq_length, embed_dim)
+        pos = torch.arange(0, max_seq_length, dtype=torch.float).unsqueeze(1)
+        div = torch.exp(torch.arange(0, embed_dim, 2).float() * (-math.log(10000.0) / embed_dim))
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.positional_encoding = nn.Parameter(pe.unsqueeze(0), requires_grad=False)
+        self.embed_dropout = nn.Dropout(dropout)
+        self.layers = nn.ModuleList([TernaryBlock(layers, embed_dim, num_heads, dim_feedforward, dropout, use_rpb, s0)
+                                     for _ in range(num_layers)])
+        self.norm = nn.LayerNorm(embed_dim)
+        if use_rpb:
+            self.attention_pool = nn.Sequential(
+                layers.ResidualPrecisionBoostLinear(embed_dim, embed_dim // 2, precision_ratio=0.2, sparsity_target=s0),
+                nn.Tanh(),
+                layers.ResidualPrecisionBoostLinear(embed_dim // 2, 1, precision_ratio=0.2, sparsity_target=s0),
+                nn.Softmax(dim=1))
+        else:
+            self.attention_pool = nn.Sequential(layers.TernaryLinear(embed_dim, embed_dim // 2), nn.Tanh(),
+                                                layers.TernaryLinear(embed_dim // 2, 1), nn.Softmax(dim=1))
+        self.scaling = nn.Parameter(torch.ones(1) * 4.0)
+        # models/text_encoder.py:338-349: xavier(gain 0.8) over every >1-D parameter (this also
+        # overwrites the sinusoidal table and leaves the precision masks untouched)
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p, gain=0.8)
+        nn.init.normal_(self.embedding.weight, mean=0.0, std=0.02)
+
+    def update_sparsity(self, progress):
+        s = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
+        for layer in self.layers:
+            layer.update_sparsity(progress)
+        if self.use_rpb and hasattr(self.attention_pool[0], "sparsity_target"):
+            self.attention_pool[0].sparsity_target = s
+            self.attention_pool[2].sparsity_target = s
+
+    def forward(self, tokens, lengths=None):
+        mask = None
+        if lengths is not None:
+            if not torch.is_tensor(lengths):
+                lengths = torch.tensor(lengths, device=tokens.device)
+            mask = _lengths_to_mask(lengths, tokens.size(0), tokens.size(1), tokens.device)
+        x = self.embed_norm(self.embedding(tokens))
+        x = self.embed_dropout(x + self.positional_encoding[:, : x.size(1), :])
+        for layer in self.layers:
+            x = layer(x, key_padding_mask=mask)
+        x = self.norm(x)
+        w = self.attention_pool(x)
+        if mask is not None:
+            w = torch.softmax(w.masked_fill(mask.unsqueeze(-1), float("-inf")), dim=1)
+        feats = torch.sum(x * w, dim=1)
+        return feats * torch.clamp(self.scaling, min=1.0, max=10.0)
+
+
+class ImageEncoder(nn.Module):
+    """models/multimodal_classifier.py:12-99: ResNet18 trunk (random init here: no network) +
+    LayerNorm + ternary projector + GELU + LayerNorm + scale + L2."""
+
+    def __init__(self, layers, embed_dim=256, use_rpb=True, sparsity_target=0.3):
+        super().__init__()
+        import torchvision.models as tvm
+        self.initial_sparsity = min(0.1, sparsity_target)
+        self.target_sparsity = sparsity_target
+        trunk = tvm.resnet18(weights=None)
+        self.base_model = nn.Sequential(*list(trunk.children())[:-1])
+        self.feature_dim = 512
+        self.feature_norm = nn.LayerNorm(self.feature_dim)
+        if use_rpb:
+            self.projector = layers.ResidualPrecisionBoostLinear(self.feature_dim, embed_dim, precision_ratio=0.2,
+                                                                 sparsity_target=self.initial_sparsity)
+        else:
+            self.projector = layers.TernaryLinear(self.feature_dim, embed_dim)
+        self.activation = nn.GELU()
+        self.proj_norm = nn.LayerNorm(embed_dim)
+        self.scaling = nn.Parameter(torch.ones(1) * 4.0)
+
+    def update_sparsity(self, progress):
+        if hasattr(self.projector, "sparsity_target"):
+            self.projector.sparsity_target = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
+
+    def forward(self, x):
+        f = self.base_model(x).squeeze(-1).squeeze(-1)
+        e = self.proj_norm(self.activation(self.projector(self.feature_norm(f))))
+        e = e * torch.clamp(self.scaling, min=1.0, max=10.0)
+        return F.normalize(e, p=2, dim=1)
+
+
+class ViTImageEncoder(nn.Module):
+    """BASELINE config 4: ViT-B/16-sized ternary image tower built from the reference's own block
+    (SURVEY 8d): fp32 16x16 patch embedding, cls token, learned positions, `depth` TernaryBlocks,
+    then the same LayerNorm -> ternary projector -> GELU -> LayerNorm -> scale -> L2 head."""
+
+    def __init__(self, layers, embed_dim=768, depth=12, num_heads=12, dim_feedforward=3072, image_size=224,
+                 patch=16, dropout=0.1, use_rpb=True, sparsity_target=0.3, out_dim=None):
+        super().__init__()
+        out_dim = out_dim or embed_dim
+        self.initial_sparsity = min(0.1, sparsity_target)
+        self.target_sparsity = sparsity_target
+        self.patch_embed = nn.Conv2d(3, embed_dim, kernel_size=patch, stride=patch)
+        n_tok = (image_size // patch) ** 2 + 1
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.randn(1, n_tok, embed_dim) * 0.02)
+        self.layers = nn.ModuleList([TernaryBlock(layers, embed_dim, num_heads, dim_feedforward, dropout, use_rpb,
+                                                  self.initial_sparsity) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim)
+        self.feature_norm = nn.LayerNorm(embed_dim)
+        if use_rpb:
+            self.projector = layers.ResidualPrecisionBoostLinear(embed_dim, out_dim, precision_ratio=0.2,
+                                                                 sparsity_target=self.initial_sparsity)
+        else:
+            self.projector = layers.TernaryLinear(embed_dim, out_dim)
+        self.activation = nn.GELU()
+        self.proj_norm = nn.LayerNorm(out_dim)
+        self.scaling = nn.Parameter(torch.ones(1) * 4.0)
+
+    def update_sparsity(self, progress):
+        for layer in self.layers:
+            layer.update_sparsity(progress)
+        if hasattr(self.projector, "sparsity_target"):
+            self.projector.sparsity_target = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
+
+    def forward(self, x):
+        x = self.patch_embed(x).flatten(2).transpose(1, 2)
+        x = torch.cat([self.cls_token.expand(x.size(0), -1, -1), x], dim=1) + self.pos_embed
+        for layer in self.layers:
+            x = layer(x)
+        f = self.norm(x)[:, 0]
+        e = self.proj_norm(self.activation(self.projector(self.feature_norm(f))))
+        e = e * torch.clamp(self.scaling, min=1.0, max=10.0)
+        return F.normalize(e, p=2, dim=1)
+
+
+class RetrievalModel(nn.Module):
+    """models/multimodal_classifier.py:102-247 (ATQMultimodalRetrieval), training path only
+    (`return_embeddings=True`).  The cross-attention `fusion` module and the post-fusion branch never
+    run in train_multimodal.py and are not built; `image_projector`, `img_norm` and
+    `temperature` exist (they are parameters the optimizer sees and DDP must treat as unused)."""
+
+    def __init__(self, layers, vocab_size=10000, embed_dim=256, hidden_dim=512, vision_threshold=0.3,
+                 text_threshold=0.2, use_residual=True, image_tower="resnet18", text_heads=8, text_layers=4,
+                 max_seq_length=50, vit_cfg=None):
+        super().__init__()
+        self.use_rpb, self.embed_dim = use_residual, embed_dim
+        self.initial_vision_sparsity = min(0.1, vision_threshold)
+        self.initial_text_sparsity = min(0.1, text_threshold)
+        self.target_vision_sparsity, self.target_text_sparsity = vision_threshold, text_threshold
+        self.current_epoch, self.total_epochs = 0, 20
+        if image_tower == "resnet18":
+            self.image_encoder = ImageEncoder(layers, embed_dim, use_residual, self.initial_vision_sparsity)
+        else:
+            self.image_encoder = ViTImageEncoder(layers, use_rpb=use_residual, sparsity_target=self.initial_vision_sparsity,
+                                                 out_dim=embed_dim, **(vit_cfg or {}))
+        self.text_encoder = TextEncoder(layers, vocab_size, embed_dim, text_heads, text_layers, hidden_dim,
+                                        use_rpb=use_residual, sparsity_target=self.initial_text_sparsity,
+                                        max_seq_length=max_seq_length)
+        if use_residual:
+            self.text_projector = layers.ResidualPrecisionBoostLinear(embed_dim, embed_dim, precision_ratio=0.2,
+                                                                      sparsity_target=self.initial_text_sparsity)
+            self.image_projector = layers.ResidualPrecisionBoostLinear(embed_dim, embed_dim, precision_ratio=0.2,
+                                                                       sparsity_target=self.initial_vision_sparsity)
+        else:
+            self.text_projector = layers.TernaryLinear(embed_dim, embed_dim)
+            self.image_projector = layers.TernaryLinear(embed_dim, embed_dim)
+        self.temperature = nn.Parameter(torch.tensor(0.07))
+        self.img_norm = nn.LayerNorm(embed_dim)
+        self.text_norm = nn.LayerNorm(embed_dim)
+
+    def set_epoch(self, current_epoch, total_epochs):
+        self.current_epoch, self.total_epochs = current_epoch, total_epochs
+        progress = min(1.0, current_epoch / (total_epochs * 0.8))
+        self.image_encoder.update_sparsity(progress)
+        self.text_encoder.update_sparsity(progress)
+        if hasattr(self.text_projector, "sparsity_target"):
+            self.text_projector.sparsity_target = self.initial_text_sparsity + progress * (
+                self.target_text_sparsity - self.initial_text_sparsity)
+            self.image_projector.sparsity_target = self.initial_vision_sparsity + progress * (
+                self.target_vision_sparsity - self.initial_vision_sparsity)
+
+    def encode_image(self, image):
+        return self.image_encoder(image)
+
+    def encode_text(self, text, text_lengths=None):
+        t = self.text_norm(self.text_projector(self.text_encoder(text, text_lengths)))
+        return F.normalize(t, p=2, dim=1)
+
+    def forward(self, image, text, text_lengths=None, return_embeddings=True):
+        assert return_embeddings, "only the training path of the reference is re-created"
+        return self.encode_image(image), self.encode_text(text, text_lengths)
+
+
+class ImageClassifier(nn.Module):
+    """models/image_classifier.py:8-63 (ATQImageClassifier; BASELINE config 1)."""
+
+    def __init__(self, layers, num_classes=10, input_channels=1, use_rpb=True, sparsity_target=0.3, hidden_size=128):
+        super().__init__()
+        self.use_rpb, self.sparsity_target = use_rpb, sparsity_target
+        self.features = nn.Sequential(
+            nn.Conv2d(input_channels, 32, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(32), nn.ReLU(),
+            nn.MaxPool2d(kernel_size=2, stride=2),
+            nn.Conv2d(32, 64, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(64), nn.ReLU(),
+            nn.MaxPool2d(kernel_size=2, stride=2), nn.Flatten())
+        flat = 64 * 7 * 7
+        if use_rpb:
+            self.classifier = nn.Sequential(
+                layers.ResidualPrecisionBoostLinear(flat, hidden_size, precision_ratio=0.05, sparsity_target=sparsity_target),
+                nn.ReLU(), nn.Dropout(0.3),
+                layers.ResidualPrecisionBoostLinear(hidden_size, num_classes, precision_ratio=0.1, sparsity_target=sparsity_target))
+        else:
+            self.classifier = nn.Sequential(layers.TernaryLinear(flat, hidden_size), nn.ReLU(), nn.Dropout(0.3),
+                                            layers.TernaryLinear(hidden_size, num_classes))
+
+    def forward(self, x):
+        return self.classifier(self.features(x))  # routing in between is the identity (atq/routing.py:4-20)
+
+
+# ---------------------------------------------------------------------------------------
+# loss (utils/enhanced_contrastive.py)
+# ---------------------------------------------------------------------------------------
+
+class HardNegativeInfoNCE(nn.Module):
+    """utils/enhanced_contrastive.py:8-162.  Same maths; the per-row Python loop that fills the two
+    hard-negative masks (:118-120) is written as two scatter_ calls (identical masks)."""
+
+    def __init__(self, temperature=0.07, lambda_reg=0.02, hard_negative_weight=0.5, hardest_mining_ratio=0.5,
+                 temperature_schedule=True):
+        super().__init__()
+        self.temperature = self.base_temperature = temperature
+        self.lambda_reg, self.hard_negative_weight = lambda_reg, hard_negative_weight
+        self.hardest_mining_ratio, self.temperature_schedule = hardest_mining_ratio, temperature_schedule
+        self.current_epoch, self.total_epochs = 0, 1
+
+    def set_epoch(self, current_epoch, total_epochs):
+        self.current_epoch, self.total_epochs = current_epoch, total_epochs
+
+    def get_current_temperature(self):
+        if not self.temperature_schedule:
+            return self.temperature
+        progress = min(1.0, self.current_epoch / (self.total_epochs * 0.7))
+        hi, lo = self.base_temperature * 2.0, self.base_temperature * 0.5
+        t = hi - (hi - lo) * (1 - math.cos(progress * math.pi)) / 2
+        return max(min(t, hi), lo)
+
+    def forward(self, image_embeddings, text_embeddings, weights=None):
+        temperature = self.get_current_temperature()
+        img = F.normalize(image_embeddings, p=2, dim=1)
+        txt = F.normalize(text_embeddings, p=2, dim=1)
+        sim = torch.matmul(img, txt.t()) / temperature
+        b = img.size(0)
+        labels = torch.arange(b, device=sim.device)
+        pos_mask = torch.eye(b, device=sim.device, dtype=sim.dtype)
+        neg_mask = 1 - pos_mask
+        with torch.no_grad():
+            k = max(1, int(b * self.hardest_mining_ratio))
+            s_it = sim.clone()
+            s_it.fill_diagonal_(-float("inf"))
+            idx_it = s_it.topk(k, dim=1).indices
+            s_ti = sim.t().clone()
+            s_ti.fill_diagonal_(-float("inf"))
+            idx_ti = s_ti.topk(k, dim=1).indices
+            m_img = torch.zeros_like(sim).scatter_(1, idx_it, 1.0)
+            m_txt = torch.zeros_like(sim).scatter_(1, idx_ti, 1.0).t()
+            hard = ((m_img + m_txt) > 0).float() * neg_mask
+            easy = neg_mask - hard
+        pw = (weights if weights is not None else torch.ones(b, device=sim.device)).view(-1, 1)
+        neg_w = torch.ones_like(sim)
+        neg_w = neg_w * easy + neg_w * hard * (1.0 + self.hard_negative_weight)
+        weighted = sim * pos_mask * pw + sim * neg_w
+        image_loss = F.cross_entropy(weighted, labels)
+        text_loss = F.cross_entropy(weighted.t(), labels)
+        img_ent = -torch.mean(torch.sum(F.softmax(sim, dim=1) * F.log_softmax(sim, dim=1), dim=1))
+        txt_ent = -torch.mean(torch.sum(F.softmax(sim.t(), dim=1) * F.log_softmax(sim.t(), dim=1), dim=1))
+        return (image_loss + text_loss) / 2 + self.lambda_reg * (img_ent + txt_ent) / 2
+
+
+class ContrastiveManager:
+    """utils/enhanced_contrastive.py:269-417 (curriculum weights + compute_loss)."""
+
+    def __init__(self, criterion, curriculum_steps=3):
+        self.criterion, self.curriculum_steps = criterion, curriculum_steps
+        self.steps = self.epoch = self.total_epochs = self.curriculum_stage = 0
+
+    def set_epoch(self, epoch, total_epochs):
+        self.epoch, self.total_epochs = epoch, total_epochs
+        self.curriculum_stage = min(self.curriculum_steps - 1, int(epoch / total_epochs * self.curriculum_steps))
+
+    def get_curriculum_weight(self, similarity):
+        pos = torch.diag(similarity)
+        if self.curriculum_stage == 0:
+            return torch.sigmoid(pos * 10)
+        if self.curriculum_stage == self.curriculum_steps - 1:
+            return 1 - torch.sigmoid(pos * 10 - 5)
+        return torch.ones_like(pos)
+
+    def compute_loss(self, image_embeddings, text_embeddings):
+        self.steps += 1
+        sim = torch.matmul(F.normalize(image_embeddings, p=2, dim=1), F.normalize(text_embeddings, p=2, dim=1).t())
+        return self.criterion(image_embeddings, text_embeddings, self.get_curriculum_weight(sim))
+
+
+def oracle_layers():
+    """The CPU oracle's layer classes under the names the builders expect (reference arm / tests)."""
+    from oracle import atq_oracle as O
+    return SimpleNamespace(TernaryLinear=O.OracleTernaryLinear, ResidualPrecisionBoostLinear=O.OracleRPBLinear)
