@@ -34,6 +34,7 @@ _SIGS = {
     "atq_last_error_string": (c_char_p, []),
     "atq_device_check": (c_int, [c_int]),
     "atq_num_sms": (c_int, [c_int]),
+    "atq_kernel_launch_count": (ctypes.c_uint64, []),
     "atq_workspace_bytes_abs_stats": (c_size_t, [c_int64]),
     "atq_abs_stats": (c_int, [c_int, _P, c_int64, _P, _P, c_size_t, _P]),
     "atq_workspace_bytes_select_kth_abs": (c_size_t, [c_int64]),
@@ -80,7 +81,12 @@ if _lib.atq_abi_version() != ABI_VERSION:
 
 lib = _lib
 _checked_devices: set = set()
-gpu_launches = 0  # number of library compute calls issued (bench.py reports it)
+gpu_launches = 0  # number of library compute calls issued
+
+
+def kernel_launch_count() -> int:
+    """Kernels launched by libatq_sm100 in this process (bench.py reports the per-step delta)."""
+    return int(_lib.atq_kernel_launch_count())
 
 
 class ATQNativeError(RuntimeError):

@@ -1,0 +1,97 @@
+"""Data-parallel plumbing for ATQ training on one 8xB200 box (new work defined by BASELINE.json;
+the reference is single-process).  One process per GPU over torch.distributed (NCCL on
+NVLink 5 / NVSwitch; gloo in the CPU tests).  Exactly two exchange steps exist on this path:
+
+  C2  all-gather of the [B_local, E] image and text embeddings before the contrastive loss
+      (utils/enhanced_contrastive.py mines negatives over the whole batch);
+  C1  one all-reduce (SUM) of the parameter gradients after backward.
+
+Wiring (b) of SURVEY H9: the gather carries no gradient for remote rows, every rank evaluates the
+identical global loss and back-propagates only through its own rows, so the SUM (not the mean)
+of the per-rank parameter gradients is the gradient of the global-batch loss.
+Weights are replicated and quantized redundantly (deterministic kernels => identical T on every
+rank, no broadcast).
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> tuple:
+    """Initialise the default process group from torchrun's environment.  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def gather_embeddings(local: torch.Tensor, group=None) -> torch.Tensor:
+    """[B_local, E] -> [B_local * world, E] in rank order; only this rank's rows carry autograd."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    src = local.detach().contiguous()
+    out = torch.empty((world * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    dist.all_gather_into_tensor(out, src, group=group)
+    parts: List[torch.Tensor] = list(out.split(src.shape[0], dim=0))
+    parts[rank] = local
+    return torch.cat(parts, dim=0)
+
+
+class FlatGradAllReduce:
+    """Single flat fp32 buffer aliasing every parameter gradient that the step produces, reduced with
+    one NCCL all-reduce per bucket.  Parameters that never receive a gradient (TernaryLinear.weight,
+    modules off the training path) keep grad=None so the optimizer skips them exactly as
+    in the single-process reference."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 256 << 20, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self.flat: Optional[torch.Tensor] = None
+        self.active: List[torch.nn.Parameter] = []
+
+    def _bind(self):
+        self.active = [p for p in self.params if p.grad is not None]
+        total = sum(p.numel() for p in self.active)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.active[0].device)
+        self.views = []
+        off = 0
+        for p in self.active:
+            self.views.append(self.flat[off: off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def zero_grad(self):
+        """Use instead of optimizer.zero_grad(set_to_none=True) once bound, to keep the aliasing."""
+        if self.flat is None:
+            for p in self.params:
+                p.grad = None
+        else:
+            self.flat.zero_()
+
+    def reduce(self):
+        if self.flat is None:
+            self._bind()  # first step: discover which parameters this graph produces gradients for
+        for p, view in zip(self.active, self.views):
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():  # autograd created a fresh tensor: adopt it
+                view.copy_(p.grad)
+                p.grad = view
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
+            return
+        n = self.flat.numel()
+        for start in range(0, n, self.bucket_elems):
+            dist.all_reduce(self.flat[start: min(n, start + self.bucket_elems)], op=dist.ReduceOp.SUM, group=self.group)

@@ -1,5 +1,6 @@
 // Library-level plumbing of libatq_sm100: error text, device selection, device checks.
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace atq {
@@ -7,6 +8,10 @@ namespace atq {
 static thread_local char g_err[512] = "";
 static thread_local int g_cur_device = -1;
 static int g_sm_count[64] = {0};
+
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 char* last_error_buf() { return g_err; }
 
@@ -66,5 +71,7 @@ int atq_device_check(int device) {
 }
 
 int atq_num_sms(int device) { return atq::sm_count(device); }
+
+uint64_t atq_kernel_launch_count(void) { return (uint64_t)atq::launches(); }
 
 }  // extern "C"

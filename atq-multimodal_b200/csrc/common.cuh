@@ -19,6 +19,7 @@ void set_error(const char* fmt, ...);
 // from this library's statically linked runtime's point of view).
 int ensure_device(int device);
 int sm_count(int device);
+void note_launch(int n = 1);  // kernel-launch counter reported by atq_kernel_launch_count()
 
 #define ATQ_CHECK_ARG(cond, msg)                                   \
   do {                                                             \
@@ -44,6 +45,7 @@ int sm_count(int device);
       atq::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__)); \
       return ATQ_ECUDA;                                                                  \
     }                                                                                    \
+    atq::note_launch();                                                                  \
   } while (0)
 
 #define ATQ_ENSURE_DEVICE(dev)              \

@@ -417,6 +417,7 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
     set_error("tgemm launch failed: %s", cudaGetErrorString(e));
     return ATQ_ECUDA;
   }
+  note_launch();
   return ATQ_OK;
 }
 

@@ -208,6 +208,7 @@ static int select_batched_impl(int device, int count, const float* const* xs, co
       set_error("select: kernel launch failed: %s", cudaGetErrorString(e));
       return ATQ_ECUDA;
     }
+    note_launch(4);
   }
   return ATQ_OK;
 }

@@ -45,6 +45,7 @@ int atq_abi_version(void);                 /* bumps on any signature change */
 const char* atq_last_error_string(void);
 int atq_device_check(int device);          /* ATQ_OK iff `device` is sm_100-class */
 int atq_num_sms(int device);
+uint64_t atq_kernel_launch_count(void);   /* kernels this library has launched in this process */
 
 /* ---- A1: per-layer adaptive threshold  (atq/quantizers.py:21-38) -------------------- */
 /* K1: grid-level |W| reduction.  stats_out (device, 16 bytes): double sum|W|; float max|W|; u32 pad. */

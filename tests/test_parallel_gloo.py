@@ -1,0 +1,79 @@
+"""CPU, world_size 2 over gloo: the data-parallel wiring (embedding all-gather + summed gradient
+all-reduce) reproduces the single-process global-batch loss and gradients."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import PKG_DIR, ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from atq import parallel
+    from workloads import models as M
+    r, w, _ = parallel.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(0)  # identical init everywhere
+    enc_i, enc_t = torch.nn.Linear(12, 8), torch.nn.Linear(10, 8)
+    unused = torch.nn.Linear(3, 3)
+    params = list(enc_i.parameters()) + list(enc_t.parameters()) + list(unused.parameters())
+    g = torch.Generator().manual_seed(123)
+    xi, xt = torch.randn(6 * world, 12, generator=g), torch.randn(6 * world, 10, generator=g)
+    man = M.ContrastiveManager(M.HardNegativeInfoNCE())
+    sync = parallel.FlatGradAllReduce(params, bucket_bytes=256)  # tiny buckets: several all-reduces
+    sl = slice(6 * rank, 6 * rank + 6)
+    for step in range(2):
+        sync.zero_grad()
+        img = parallel.gather_embeddings(enc_i(xi[sl]))
+        txt = parallel.gather_embeddings(enc_t(xt[sl]))
+        assert img.shape == (6 * world, 8)
+        loss = man.compute_loss(img, txt)
+        loss.backward()
+        sync.reduce()
+    assert unused.weight.grad is None  # never bound: optimizer would skip it
+    torch.save({"loss": loss.detach(), "grads": [p.grad.clone() for p in params[:4]]}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dp_matches_single_process(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from workloads import models as M
+    torch.manual_seed(0)
+    enc_i, enc_t = torch.nn.Linear(12, 8), torch.nn.Linear(10, 8)
+    g = torch.Generator().manual_seed(123)
+    xi, xt = torch.randn(6 * world, 12, generator=g), torch.randn(6 * world, 10, generator=g)
+    man = M.ContrastiveManager(M.HardNegativeInfoNCE())
+    loss = man.compute_loss(enc_i(xi), enc_t(xt))
+    loss.backward()
+    want = [p.grad for p in list(enc_i.parameters()) + list(enc_t.parameters())]
+    r0, r1 = (torch.load(tmp_path / f"r{r}.pt") for r in range(world))
+    assert torch.allclose(r0["loss"], loss.detach(), atol=1e-6) and torch.allclose(r1["loss"], loss.detach(), atol=1e-6)
+    for a, b, w in zip(r0["grads"], r1["grads"], want):
+        assert torch.equal(a, b)  # all-reduced: identical on every rank
+        assert torch.allclose(a, w, atol=1e-5, rtol=1e-4)
+
+
+def test_gather_is_identity_without_process_group():
+    from atq import parallel
+    x = torch.randn(3, 4, requires_grad=True)
+    assert parallel.gather_embeddings(x) is x
+    assert parallel.init_from_env() == (0, 1, 0)

@@ -1,0 +1,120 @@
+"""Synthetic training steps for the BASELINE.json configs (bench / test harness).
+
+Step bodies follow the reference's loops on synthetic tensors of the named shapes
+(SURVEY.md 8d): train.py:170-212 (config 1) and train_multimodal.py:540-585 (configs 2 and 4),
+with GradualQuantizationScheduler.step driven explicitly (the reference rebinds `scheduler` to the
+LR scheduler at train_multimodal.py:403, so its quantization schedule never runs -- SURVEY 3.3;
+BASELINE config 2 says "gradual quant", so the harness applies the intended behaviour)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+from . import models as M
+
+
+@dataclass
+class RetrievalCfg:
+    name: str
+    vocab: int = 3000
+    embed_dim: int = 192
+    hidden_dim: int = 384
+    image_size: int = 160
+    seq_len: int = 50
+    batch: int = 16            # per-GPU batch
+    image_tower: str = "resnet18"
+    text_heads: int = 8
+    text_layers: int = 4
+    total_epochs: int = 10
+    epoch: int = 5             # mid-schedule: per-layer sparsities differ
+    warmup_epochs: int = 2
+    lr: float = 5e-5
+    min_len: int = 5
+    max_len: int = 20
+
+
+FLICKR8K_SHAPE = RetrievalCfg(name="train_multimodal.py synthetic Flickr8k shape: image 160, embed 192, hidden 384, "
+                                   "batch 16, gradual quant + residual")
+VITB16 = RetrievalCfg(name="ViT-B/16-sized ternary image encoder + 12-layer ternary text encoder, contrastive "
+                           "batch 512 per GPU (4096 across 8xB200)",
+                      embed_dim=768, hidden_dim=3072, image_size=224, batch=512, image_tower="vit",
+                      text_heads=12, text_layers=12, max_len=50)
+
+
+def build_retrieval(layers, cfg: RetrievalCfg, seed=42):
+    torch.manual_seed(seed)  # identical init on every rank (SURVEY 8e determinism)
+    model = M.RetrievalModel(layers, cfg.vocab, cfg.embed_dim, cfg.hidden_dim, 0.3, 0.2, True,
+                             image_tower=cfg.image_tower, text_heads=cfg.text_heads, text_layers=cfg.text_layers,
+                             max_seq_length=cfg.seq_len,
+                             vit_cfg=dict(embed_dim=cfg.embed_dim, depth=12, num_heads=12, dim_feedforward=cfg.hidden_dim,
+                                          image_size=cfg.image_size) if cfg.image_tower == "vit" else None)
+    criterion = M.HardNegativeInfoNCE(temperature=0.07, lambda_reg=0.02, hard_negative_weight=0.5,
+                                      temperature_schedule=True)
+    manager = M.ContrastiveManager(criterion)
+    criterion.set_epoch(cfg.epoch, cfg.total_epochs)
+    manager.set_epoch(cfg.epoch, cfg.total_epochs)
+    return model, criterion, manager
+
+
+def make_optimizer(model, cfg: RetrievalCfg):
+    return torch.optim.AdamW(model.parameters(), lr=cfg.lr, weight_decay=1e-4, betas=(0.9, 0.98))
+
+
+def synthetic_batches(cfg: RetrievalCfg, count, seed, pin=False):
+    """`count` host batches (images fp32, captions int64, lengths int64) of the config's shape."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(count):
+        images = torch.randn(cfg.batch, 3, cfg.image_size, cfg.image_size, generator=g)
+        captions = torch.randint(4, cfg.vocab, (cfg.batch, cfg.seq_len), generator=g)
+        lengths = torch.randint(cfg.min_len, cfg.max_len, (cfg.batch,), generator=g)
+        if pin:
+            images, captions, lengths = images.pin_memory(), captions.pin_memory(), lengths.pin_memory()
+        out.append((images, captions, lengths))
+    return out
+
+
+def retrieval_step(model, manager, optimizer, batch, gather=None, grad_sync=None):
+    """One optimisation step; returns the loss tensor (still on the device)."""
+    images, captions, lengths = batch
+    if grad_sync is not None:
+        grad_sync.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=True)
+    img, txt = model(images, captions, lengths, return_embeddings=True)
+    if gather is not None:
+        img, txt = gather(img), gather(txt)
+    loss = manager.compute_loss(img, txt)
+    loss.backward()
+    if grad_sync is not None:
+        grad_sync.reduce()
+    optimizer.step()
+    return loss
+
+
+# ---- config 1 -------------------------------------------------------------------------
+
+def build_classifier(layers, seed=0):
+    torch.manual_seed(seed)
+    return M.ImageClassifier(layers, num_classes=10, input_channels=1, use_rpb=True, sparsity_target=0.3, hidden_size=128)
+
+
+def classifier_batches(count, seed=0, batch=256, pin=False):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(count):
+        x = torch.randn(batch, 1, 28, 28, generator=g)
+        y = torch.randint(0, 10, (batch,), generator=g)
+        out.append((x.pin_memory(), y.pin_memory()) if pin else (x, y))
+    return out
+
+
+def classifier_step(model, optimizer, batch):
+    x, y = batch
+    optimizer.zero_grad(set_to_none=True)
+    loss = F.cross_entropy(model(x), y)
+    loss.backward()
+    optimizer.step()
+    return loss
