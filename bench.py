@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- multimodal ATQ training throughput on B200 (BASELINE.json metric), with the
+roofline of the dominant hot-path kernel and the reference algorithm's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload flickr8k|vitb16] [--mode parity|fast]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+A "step" is one optimisation step of the named synthetic config (forward through every ternary
+layer, contrastive loss, backward, gradient all-reduce when N > 1, AdamW).
+  value : whole-job samples/s with the batch already resident in HBM
+  e2e   : the same step with the batch copied from pinned host memory and the loss read back
+  roofline / rooflines : CUDA-event timings of this library's kernels (in the step, and at the
+          BASELINE config-3 / config-5 shapes) against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the CPU port of the reference algorithm (oracle/) on the same
+          config, on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "atq-multimodal_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "multimodal ATQ train samples/sec"
+UNIT = "samples/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------
+class L2Flusher:
+    def __init__(self, device, nbytes=256 << 20):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def __call__(self):
+        self.buf.zero_()  # 256 MB write > 126 MB L2
+
+
+def to_device(batch, device):
+    return tuple(t.to(device, non_blocking=True) for t in batch)
+
+
+def max_over_ranks(x, device, world):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def timed_steps(step_fn, steps, flush, world):
+    """K steps, each bracketed by CUDA events on the current stream; the L2 flush runs between steps,
+    outside the events.  Returns total device milliseconds over the K steps (this rank)."""
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    barrier(world)
+    for i in range(steps):
+        flush()
+        starts[i].record()
+        step_fn(i)
+        ends[i].record()
+    barrier(world)
+    return sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+
+
+# ---------------------------------------------------------------------------------------
+# CPU port of the reference (oracle) on the same config
+# ---------------------------------------------------------------------------------------
+def cpu_port_throughput(cfg, steps, warmup):
+    from oracle import policy as P
+    from workloads import models as M
+    from workloads import train as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    model, _, manager = T.build_retrieval(M.oracle_layers(), cfg)
+    P.scheduler_step(model, cfg.epoch, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs)
+    opt = T.make_optimizer(model, cfg)
+    batches = T.synthetic_batches(cfg, 2, seed=42)
+    model.train()
+    for i in range(warmup):
+        float(T.retrieval_step(model, manager, opt, batches[i % 2]).detach())
+    t0 = time.perf_counter()
+    for i in range(steps):
+        float(T.retrieval_step(model, manager, opt, batches[i % 2]).detach())
+    dt = time.perf_counter() - t0
+    return cfg.batch * steps / dt, dt / steps
+
+
+# ---------------------------------------------------------------------------------------
+# kernel-level rooflines measured live (CUDA events, this process)
+# ---------------------------------------------------------------------------------------
+def _event_time(fn, iters, flush=None):
+    fn()
+    torch.cuda.synchronize()
+    total = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        total += s.elapsed_time(e)
+    return total / iters  # ms
+
+
+def kernel_rooflines(device, peaks, flush, quick=True):
+    """BASELINE config 3 (GEMM, tensor-bound) and config 5 (quantize/pack, HBM-bound) shapes."""
+    import atq._engine as eng
+    out = []
+    hbm, tf = peaks["hbm_gbs"], peaks["bf16_tflops"]
+    src = "of measured" if peaks["_source"] == "measured" else "of fallback"
+    # ---- config 3: TernaryLinear forward GEMM, 4096x4096 packed weights, 8192 tokens
+    M = K = 4096
+    N = 8192
+    g = torch.Generator(device=device).manual_seed(0)
+    w = (torch.rand(M, K, device=device, generator=g) * 2 - 1) / K ** 0.5
+    x = torch.randn(N, K, device=device, generator=g)
+    thr = eng.adaptive_threshold(w, 0.3)
+    tb = torch.empty((M, K), dtype=torch.bfloat16, device=device)
+    tbt = torch.empty((K, M), dtype=torch.bfloat16, device=device)
+    import atq._native as nv
+    nv.call("atq_build_ternary_operands", 0 if device.index is None else device.index, w.data_ptr(), M, K, thr.data_ptr(),
+            None, tb.data_ptr(), K, tbt.data_ptr(), M, None, nv.stream_ptr(device.index or 0))
+    for mode, want_lo in (("parity(hi+lo)", True), ("fast(bf16)", False)):
+        xa = eng.split_bf16(x, want_lo)
+        ms = _event_time(lambda: eng.tgemm(xa, (tb, None, K), N, M, K), 5, flush)
+        ach = 2.0 * N * M * K / (ms * 1e-3) / 1e12
+        out.append({"kernel": f"tgemm_kernel fwd {mode}", "workload": f"config3 TernaryLinear {M}x{K}, {N} tokens",
+                    "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
+                    "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None})
+    # ---- config 5: quantize + pack, one 4096x4096 layer (64 MiB fp32; L2 flushed between runs)
+    n = M * K
+    ms = _event_time(lambda: eng.adaptive_threshold(w, 0.3), 5, flush)
+    out.append({"kernel": "select_pass_kernel x3 (exact k-th |W|)", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
+                "achieved": round(4.0 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(4.0 * n / (ms * 1e-3) / 1e9 / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4),
+                "traffic": None, "note": "4 B/elem over the whole 3-pass select"})
+    ms = _event_time(lambda: eng.ternarize_pack2(w, thr), 5, flush)
+    out.append({"kernel": "ternarize_kernel -> 2-bit", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
+                "achieved": round(4.25 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(4.25 * n / (ms * 1e-3) / 1e9 / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4), "traffic": None})
+    packed = eng.ternarize_pack2(w, thr)
+    ms = _event_time(lambda: eng.unpack2(packed, n), 5, flush)
+    out.append({"kernel": "unpack2_kernel -> fp32", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
+                "achieved": round(4.25 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
+                "frac": round(4.25 * n / (ms * 1e-3) / 1e9 / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4), "traffic": None})
+    return out
+
+
+class CallProfiler:
+    """Brackets every C-ABI call with CUDA events (a separate, untimed pass of the same step)."""
+
+    FLOPS = {"atq_tgemm": lambda a: 2.0 * a[0] * a[1] * a[2], "atq_tgemm_dw_masked": lambda a: 2.0 * a[0] * a[1] * a[2]}
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        import atq._native as nv
+        self.nv, self.orig = nv, nv.call
+
+        def wrapped(name, *args):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            self.orig(name, *args)
+            e.record()
+            self.records.append((name, tuple(a for a in args[1:4] if isinstance(a, int)), s, e))
+
+        nv.call = wrapped
+        import atq._engine as eng
+        eng.nv.call = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        self.nv.call = self.orig
+        torch.cuda.synchronize()
+
+    def summary(self):
+        by = {}
+        for name, key, s, e in self.records:
+            d = by.setdefault(name, {"ms": 0.0, "calls": 0, "flops": 0.0})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            if name in self.FLOPS and len(key) == 3:
+                d["flops"] += self.FLOPS[name](key)
+        return by
+
+
+# ---------------------------------------------------------------------------------------
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, s_per_step = cpu_port_throughput(cfg, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(s_per_step * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.name, "per_gpu_batch": cfg.batch, "device": "cpu"},
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full optimisation steps of the same config (batch {cfg.batch}) on "
+                                       f"the CPU port of the reference algorithm (oracle/, torch CPU, {cores} threads)"},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, cfg):
+    import atq
+    import atq._native as nv
+    from atq import parallel
+    from atq.mixed_precision_atq import GradualQuantizationScheduler
+    from workloads import train as T
+
+    rank, world, local = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    atq.set_gemm_mode(args.mode)
+    peaks = load_peaks()
+
+    model, _, manager = T.build_retrieval(atq, cfg)
+    model.to(device).train()
+    GradualQuantizationScheduler(model, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs).step(cfg.epoch)
+    opt = T.make_optimizer(model, cfg)
+    sync = parallel.FlatGradAllReduce(model.parameters()) if world > 1 else None
+    gather = parallel.gather_embeddings if world > 1 else None
+
+    pool = 4
+    host = T.synthetic_batches(cfg, pool, seed=42 + rank, pin=True)
+    resident = [to_device(b, device) for b in host]
+    flush = L2Flusher(device)
+    losses = []
+
+    def step_resident(i):
+        losses.append(T.retrieval_step(model, manager, opt, resident[i % pool], gather, sync))
+
+    def step_e2e(i):
+        batch = to_device(host[i % pool], device)
+        losses.append(float(T.retrieval_step(model, manager, opt, batch, gather, sync).detach()))
+
+    for i in range(args.warmup):
+        step_resident(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    k0 = nv.kernel_launch_count()
+    ms_total = timed_steps(step_resident, args.steps, flush, world)
+    launches = nv.kernel_launch_count() - k0
+    ms_total = max_over_ranks(ms_total, device, world)
+    step_e2e(0)
+    ms_e2e = max_over_ranks(timed_steps(step_e2e, args.steps, flush, world), device, world)
+    clocks = sampler.stop()
+
+    global_batch = cfg.batch * world
+    value = global_batch * args.steps / (ms_total * 1e-3)
+    e2e_value = global_batch * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    final_loss = float(losses[-1]) if losses else float("nan")
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": cfg.name, "per_gpu_batch": cfg.batch, "global_batch": global_batch,
+                       "parallelism": f"dp{world}", "gemm_mode": args.mode,
+                       "gemm_arithmetic": "bf16 hi+lo operand pairs, fp32 TMEM accumulate" if args.mode == "parity"
+                       else "bf16 operands, fp32 TMEM accumulate",
+                       "quant_schedule": f"GradualQuantizationScheduler epoch {cfg.epoch}/{cfg.total_epochs}",
+                       "l2": "flushed between timed steps (256 MB write, outside the per-step events)"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(ms_e2e / args.steps, 4)},
+            "gpu_launches": int(launches), "clocks": clocks, "final_loss": round(final_loss, 5)}
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel of THIS library inside the step (separate untimed pass)
+        prof = CallProfiler()
+        with prof:
+            for i in range(2):
+                step_resident(i)
+        summ = prof.summary()
+        own_ms = sum(d["ms"] for d in summ.values()) / 2
+        top = max(summ.items(), key=lambda kv: kv[1]["ms"]) if summ else None
+        tf_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        src = "of measured" if peaks["_source"] == "measured" else "of fallback"
+        if top is not None:
+            name, d = top
+            if d["flops"] > 0:
+                ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+                line["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": tf_peak,
+                                    "unit": "TFLOP/s", "frac": round(ach / tf_peak, 5), "traffic": None,
+                                    "peak_kind": f"bf16 sustained {src}", "calls_per_step": d["calls"] // 2,
+                                    "ms_per_step": round(d["ms"] / 2, 4),
+                                    "share_of_own_kernel_time": round(d["ms"] / 2 / max(own_ms, 1e-9), 3),
+                                    "note": "useful flops 2*rows*cols*k per call; shapes of this config are "
+                                            "launch/latency bound (SURVEY H10) -- see rooflines[] for config 3/5 shapes"}
+            else:
+                line["roofline"] = {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"],
+                                    "unit": "GB/s", "frac": None, "traffic": None, "ms_per_step": round(d["ms"] / 2, 4)}
+        line["own_kernel_ms_per_step"] = round(own_ms, 4)
+        line["own_calls"] = {k: {"calls_per_step": v["calls"] // 2, "ms_per_step": round(v["ms"] / 2, 4)} for k, v in
+                             sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+        if world == 1 and not args.no_kernel_rooflines:
+            line["rooflines"] = kernel_rooflines(device, peaks, flush)
+        if world == 1 and not args.no_cpu_baseline:
+            v, s_per = cpu_port_throughput(cfg, args.cpu_steps, 1)
+            line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{args.cpu_steps} full optimisation steps of the same config (batch "
+                                              f"{cfg.batch}) on the CPU port of the reference algorithm (oracle/), "
+                                              f"{round(s_per, 3)} s/step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=["flickr8k", "vitb16"], default="flickr8k")
+    ap.add_argument("--mode", choices=["parity", "fast"], default="parity")
+    ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (debug only; invalidates the number)")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-rooflines", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    from workloads import train as T
+    import dataclasses
+    cfg = T.FLICKR8K_SHAPE if args.workload == "flickr8k" else T.VITB16
+    if args.batch:
+        cfg = dataclasses.replace(cfg, batch=args.batch, name=cfg.name + f" [DEBUG batch {args.batch}]")
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

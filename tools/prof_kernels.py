@@ -1,0 +1,41 @@
+"""Short driver for ncu: runs each hot-path kernel a few times at BASELINE config 3 / 5 shapes."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "atq-multimodal_b200")):
+    sys.path.insert(0, p)
+import torch
+import atq
+import atq._engine as eng
+
+dev = torch.device("cuda:0")
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+M = K = 4096
+N = 8192
+g = torch.Generator(device=dev).manual_seed(0)
+w = (torch.rand(M, K, device=dev, generator=g) * 2 - 1) / K ** 0.5
+x = torch.randn(N, K, device=dev, generator=g)
+gy = torch.randn(N, M, device=dev, generator=g)
+reps = 3
+if which in ("all", "stream"):
+    for _ in range(reps):
+        thr = eng.adaptive_threshold(w, 0.3)
+        packed = eng.ternarize_pack2(w, thr)
+        t = eng.ternarize_f32(w, thr)
+        u = eng.unpack2(packed, M * K)
+        p2, flag = eng.pack2_from_f32(u)
+        xa = eng.split_bf16(x, True)
+        xt = eng.split_bf16_t(x, True)
+if which in ("all", "gemm"):
+    tl = atq.TernaryLinear(K, M).to(dev)
+    rpb = atq.ResidualPrecisionBoostLinear(K, M, 0.05, True, 0.3).to(dev)
+    for mode in ("parity", "fast"):
+        atq.set_gemm_mode(mode)
+        for mod in (tl, rpb):
+            for _ in range(reps):
+                xi = x.clone().requires_grad_(True)
+                y = mod(xi)
+                y.backward(gy)
+torch.cuda.synchronize()
+print("done")
