@@ -292,6 +292,30 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
     return cache
 
 
+@torch.no_grad()
+def prepare_quantization(model, threshold_factor=0.05) -> int:
+    """Re-quantize every ternary layer of `model` whose weights / alpha / mask / sparsity target
+    changed since its operands were built, with ONE batched threshold launch sequence for all of
+    them (3 radix passes over all layers instead of 3 per layer).  Optional: the layers quantize
+    lazily on their own if this is never called.  Returns the number of layers rebuilt."""
+    stale = []
+    for m in model.modules():
+        cache = getattr(m, "_ops", None)
+        if not isinstance(cache, LayerOperands) or not m.weight.is_cuda:
+            continue
+        mask = getattr(m, "precision_mask", None)
+        s = getattr(m, "sparsity_target", 0.3)
+        alpha = m.alpha if mask is not None else None
+        if cache.key != _key(m.weight, alpha, mask, s, threshold_factor):
+            stale.append((m, cache, alpha, mask, s))
+    if not stale:
+        return 0
+    thr = adaptive_threshold_batched([m.weight.detach() for m, *_ in stale], [s for *_, s in stale], threshold_factor)
+    for i, (m, cache, alpha, mask, s) in enumerate(stale):
+        layer_operands(cache, m.weight, m.alpha, mask, s, threshold_factor, thr=thr[i])
+    return len(stale)
+
+
 # ---------------------------------------------------------------------------------------
 # autograd nodes
 # ---------------------------------------------------------------------------------------

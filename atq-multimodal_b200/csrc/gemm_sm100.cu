@@ -245,72 +245,57 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
   } else {
     // ================= epilogue warps 2..5 =================
+    // TMEM gives each thread one accumulator ROW (32 columns per tcgen05.ld).  Rows are staged
+    // through shared memory (the pipeline stages are idle once tmem_full fires) so that every
+    // global access below is a warp-wide 128-byte row segment: lane = column.
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
     mbar_wait(tmem_full_bar, 0);
     tcgen05_fence_after();
-    const int64_t r = m0 + quarter * 32 + lane;
-    const bool row_ok = r < p.rows;
+    float* stg = reinterpret_cast<float*>(smem_gen) + (warp_idx - 2) * (32 * 33);  // [32][33] per warp
+    const int64_t r_base = m0 + quarter * 32;
     const float scale = (EPI == EPI_LINEAR && p.scale != nullptr) ? __ldg(p.scale) : 1.f;
     float partial = 0.f;
-    const bool vec_out = ((p.out_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15u) == 0);
 #pragma unroll 1
     for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-      const int64_t c = n0 + ch * 32;
-      if (c >= p.cols) break;  // warp-uniform
+      const int64_t c0 = n0 + ch * 32;
+      if (c0 >= p.cols || r_base >= p.rows) break;  // warp-uniform
       uint32_t acc[32];
       tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), acc);
       tmem_ld_wait();
-      const bool full_chunk = (c + 32 <= p.cols);
-      if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(acc[j]);  // bank (lane+j)%32: conflict-free
+      __syncwarp();
+      const int64_t c = c0 + lane;
+      const bool col_ok = c < p.cols;
+      const int rows_here = (int)((p.rows - r_base) < 32 ? (p.rows - r_base) : 32);
       if constexpr (EPI == EPI_LINEAR) {
-        float* orow = p.out + r * p.out_pitch + c;
-        const float* rrow = p.dot_ref ? p.dot_ref + r * p.dot_ref_pitch + c : nullptr;
-        if (full_chunk && vec_out) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
-                                   __uint_as_float(acc[j + 3]));
-            if (rrow) {
-              partial += v.x * __ldg(rrow + j) + v.y * __ldg(rrow + j + 1) + v.z * __ldg(rrow + j + 2) + v.w * __ldg(rrow + j + 3);
-            }
-            v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
-            if (p.bias) {
-              v.x += __ldg(p.bias + c + j); v.y += __ldg(p.bias + c + j + 1);
-              v.z += __ldg(p.bias + c + j + 2); v.w += __ldg(p.bias + c + j + 3);
-            }
-            *reinterpret_cast<float4*>(orow + j) = v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (c + j < p.cols) {
-              float v = __uint_as_float(acc[j]);
-              if (rrow) partial += v * __ldg(rrow + j);
-              v *= scale;
-              if (p.bias) v += __ldg(p.bias + c + j);
-              orow[j] = v;
-            }
+        const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + c) : 0.f;
+        if (col_ok) {
+#pragma unroll 8
+          for (int rr = 0; rr < rows_here; ++rr) {
+            const int64_t r = r_base + rr;
+            float v = stg[rr * 33 + lane];
+            if (p.dot_ref != nullptr) partial += v * __ldg(p.dot_ref + r * p.dot_ref_pitch + c);
+            p.out[r * p.out_pitch + c] = v * scale + bias;
           }
         }
       } else {
-        float* orow = p.out + r * p.out_pitch + c;
-        const int64_t flat0 = r * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (c + j < p.cols) {
-            const float g = __uint_as_float(acc[j]);
-            const float mk = p.mask ? __ldg(p.mask + flat0 + j) : 1.f;
-            if (p.tern) {
-              const int64_t i = flat0 + j;
+        if (col_ok) {
+#pragma unroll 8
+          for (int rr = 0; rr < rows_here; ++rr) {
+            const int64_t r = r_base + rr;
+            const int64_t i = r * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
+            const float g = stg[rr * 33 + lane];
+            const float mk = p.mask ? __ldg(p.mask + i) : 1.f;
+            if (p.tern != nullptr) {
               const uint32_t code = ((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u;
               partial += g * ((float)code - 1.f) * (1.f - mk);
             }
-            orow[j] = g * mk;
+            p.out[r * p.out_pitch + c] = g * mk;
           }
         }
       }
-      }  // row_ok
-      __syncwarp();  // reconverge before the next warp-aligned tcgen05.ld
+      __syncwarp();  // staging buffer reuse + reconverge before the next warp-aligned tcgen05.ld
     }
     if (p.partials != nullptr) {
       partial = warp_sum(partial);

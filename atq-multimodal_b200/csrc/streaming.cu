@@ -379,17 +379,27 @@ __global__ void __launch_bounds__(256)
   const int64_t k0 = (int64_t)blockIdx.x * kTile, m0 = (int64_t)blockIdx.y * kTile;
   unsigned long long nnz = 0;
   double swt = 0.0;
-#pragma unroll 4
-  for (int rr = ty; rr < kTile; rr += 4) {
-    int64_t m = m0 + rr, k = k0 + tx;
+  // all 16 (+16 mask) loads of this thread are issued before any of them is consumed
+  float xs[kTile / 4], mks[kTile / 4];
+#pragma unroll
+  for (int it = 0; it < kTile / 4; ++it) {
+    const int64_t m = m0 + ty + 4 * it, k = k0 + tx;
+    const bool ok = (m < M && k < K);
+    xs[it] = ok ? __ldg(w + m * K + k) : 0.f;
+    if constexpr (MIXED) mks[it] = ok ? __ldg(mask + m * K + k) : 0.f;
+  }
+#pragma unroll
+  for (int it = 0; it < kTile / 4; ++it) {
+    const int rr = ty + 4 * it;
+    const int64_t m = m0 + rr, k = k0 + tx;
     float val = 0.f;
     uint32_t c = 1u;
     if (m < M && k < K) {
-      float x = __ldg(w + m * K + k);
+      const float x = xs[it];
       c = tern_code(x, thr);
-      float t = (float)c - 1.f;
+      const float t = (float)c - 1.f;
       if constexpr (MIXED) {
-        float mk = __ldg(mask + m * K + k);
+        const float mk = mks[it];
         // same expression order as the reference: ((T*alpha)*(1-mask)) + (W*mask), fp32
         val = (t * alpha) * (1.f - mk) + x * mk;
       } else {
@@ -481,6 +491,31 @@ __global__ void __launch_bounds__(256)
   float t = 0.f;
   for (int64_t p = 0; p < nparts; ++p) t += part[p * cols + c];
   out[c] = t;
+}
+
+// small-N path: one CTA per 32 columns walks every row (single launch, deterministic)
+__global__ void __launch_bounds__(256)
+    colsum_small_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ out) {
+  __shared__ float s[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  float acc0 = 0.f, acc1 = 0.f;
+  if (c < cols) {
+    int64_t r = wid;
+    for (; r + 8 < rows; r += 16) {
+      acc0 += __ldg(x + r * ld + c);
+      acc1 += __ldg(x + (r + 8) * ld + c);
+    }
+    if (r < rows) acc0 += __ldg(x + r * ld + c);
+  }
+  s[wid][lane] = acc0 + acc1;
+  __syncthreads();
+  if (wid == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][lane];
+    out[c] = t;
+  }
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -680,6 +715,11 @@ int atq_colsum_f32(int device, const float* x, int64_t rows, int64_t cols, int64
     return ATQ_EWORKSPACE;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows <= 4096) {
+    colsum_small_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>(x, rows, cols, ld, out);
+    ATQ_LAUNCH_CHECK();
+    return ATQ_OK;
+  }
   int64_t parts = (rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta;
   dim3 g1((unsigned)((cols + 31) / 32), (unsigned)parts);
   ATQ_CHECK_ARG(parts <= 65535, "rows too large for one launch");

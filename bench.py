@@ -305,7 +305,8 @@ def run_ours(args, cfg):
     model, _, manager = T.build_retrieval(atq, cfg)
     model.to(device).train()
     GradualQuantizationScheduler(model, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs).step(cfg.epoch)
-    opt = T.make_optimizer(model, cfg)
+    use_graph = not args.no_graph
+    opt = T.make_optimizer(model, cfg, capturable=use_graph)
     sync = parallel.FlatGradAllReduce(model.parameters()) if world > 1 else None
     gather = parallel.gather_embeddings if world > 1 else None
 
@@ -315,22 +316,39 @@ def run_ours(args, cfg):
     flush = L2Flusher(device)
     losses = []
 
+    def eager_step(batch):
+        return T.retrieval_step(model, manager, opt, batch, gather, sync, atq.prepare_quantization)
+
+    run_step = eager_step
+    for i in range(args.warmup):
+        eager_step(resident[i % pool])
+    torch.cuda.synchronize()
+    gstep = None
+    if use_graph:
+        # the whole step (quantize + forward + loss + backward [+ all-reduce] + AdamW) as one CUDA graph
+        gstep = T.GraphedRetrievalStep(model, manager, opt, resident[0], gather, sync, prepare=atq.prepare_quantization)
+        run_step = gstep
+        for i in range(2):
+            run_step(resident[i % pool])
+        torch.cuda.synchronize()
+
     def step_resident(i):
-        losses.append(T.retrieval_step(model, manager, opt, resident[i % pool], gather, sync))
+        losses.append(run_step(resident[i % pool]).detach())
 
     def step_e2e(i):
-        batch = to_device(host[i % pool], device)
-        losses.append(float(T.retrieval_step(model, manager, opt, batch, gather, sync).detach()))
-
-    for i in range(args.warmup):
-        step_resident(i)
-    torch.cuda.synchronize()
+        if gstep is not None:
+            loss = gstep(host[i % pool])          # pinned host -> static device buffers, then replay
+        else:
+            loss = eager_step(to_device(host[i % pool], device))
+        losses.append(float(loss.detach()))       # device -> host read of the step's loss
 
     sampler = ClockSampler(local)
     sampler.start()
     k0 = nv.kernel_launch_count()
     ms_total = timed_steps(step_resident, args.steps, flush, world)
     launches = nv.kernel_launch_count() - k0
+    if gstep is not None:
+        launches = gstep.own_kernels_per_replay * args.steps  # replays re-launch the captured kernels
     ms_total = max_over_ranks(ms_total, device, world)
     step_e2e(0)
     ms_e2e = max_over_ranks(timed_steps(step_e2e, args.steps, flush, world), device, world)
@@ -350,6 +368,7 @@ def run_ours(args, cfg):
                        "gemm_arithmetic": "bf16 hi+lo operand pairs, fp32 TMEM accumulate" if args.mode == "parity"
                        else "bf16 operands, fp32 TMEM accumulate",
                        "quant_schedule": f"GradualQuantizationScheduler epoch {cfg.epoch}/{cfg.total_epochs}",
+                       "execution": "whole step captured in one CUDA graph" if use_graph else "eager",
                        "l2": "flushed between timed steps (256 MB write, outside the per-step events)"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / args.steps, 4)},
@@ -357,10 +376,12 @@ def run_ours(args, cfg):
 
     if rank == 0:
         # ---- roofline of the dominant kernel of THIS library inside the step (separate untimed pass)
+        if gstep is not None:
+            gstep.release()
         prof = CallProfiler()
         with prof:
             for i in range(2):
-                step_resident(i)
+                eager_step(resident[i % pool])
         summ = prof.summary()
         own_ms = sum(d["ms"] for d in summ.values()) / 2
         top = max(summ.items(), key=lambda kv: kv[1]["ms"]) if summ else None
@@ -408,6 +429,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (debug only; invalidates the number)")
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -212,3 +212,23 @@ def test_fast_mode_is_bf16_single_term():
         atq.set_gemm_mode("parity")
     xb = x.bfloat16().float()
     assert torch.allclose(y, ref(xb).detach(), rtol=1e-3, atol=1e-3)
+
+
+def test_prepare_quantization_batched_equals_lazy():
+    torch.manual_seed(5)
+    ref = torch.nn.Sequential(O.OracleRPBLinear(192, 96, 0.2, True, 0.1333), torch.nn.Tanh(), O.OracleRPBLinear(96, 1, 0.2, True, 0.1),
+                              torch.nn.Tanh(), O.OracleTernaryLinear(1, 8))
+    mod = torch.nn.Sequential(atq.ResidualPrecisionBoostLinear(192, 96, 0.2, True, 0.1333), torch.nn.Tanh(),
+                              atq.ResidualPrecisionBoostLinear(96, 1, 0.2, True, 0.1), torch.nn.Tanh(), atq.TernaryLinear(1, 8))
+    mod.load_state_dict(ref.state_dict())
+    mod.to(DEV)
+    x = torch.randn(40, 192)
+    assert atq.prepare_quantization(mod) == 3
+    assert atq.prepare_quantization(mod) == 0  # nothing stale
+    with torch.no_grad():
+        assert torch.allclose(mod(x.to(DEV)).cpu(), ref(x), **TOL)
+        mod[0].sparsity_target = ref[0].sparsity_target = 0.4
+        ref[2].weight.mul_(1.5)
+        mod[2].weight.copy_(ref[2].weight)
+        assert atq.prepare_quantization(mod) == 2
+        assert torch.allclose(mod(x.to(DEV)).cpu(), ref(x), **TOL)

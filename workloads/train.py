@@ -58,8 +58,9 @@ def build_retrieval(layers, cfg: RetrievalCfg, seed=42):
     return model, criterion, manager
 
 
-def make_optimizer(model, cfg: RetrievalCfg):
-    return torch.optim.AdamW(model.parameters(), lr=cfg.lr, weight_decay=1e-4, betas=(0.9, 0.98))
+def make_optimizer(model, cfg: RetrievalCfg, capturable=False):
+    return torch.optim.AdamW(model.parameters(), lr=cfg.lr, weight_decay=1e-4, betas=(0.9, 0.98),
+                             capturable=capturable)
 
 
 def synthetic_batches(cfg: RetrievalCfg, count, seed, pin=False):
@@ -76,13 +77,15 @@ def synthetic_batches(cfg: RetrievalCfg, count, seed, pin=False):
     return out
 
 
-def retrieval_step(model, manager, optimizer, batch, gather=None, grad_sync=None):
+def retrieval_step(model, manager, optimizer, batch, gather=None, grad_sync=None, prepare=None):
     """One optimisation step; returns the loss tensor (still on the device)."""
     images, captions, lengths = batch
     if grad_sync is not None:
         grad_sync.zero_grad()
     else:
         optimizer.zero_grad(set_to_none=True)
+    if prepare is not None:
+        prepare(model)  # batched re-quantization of every layer the last optimizer step touched
     img, txt = model(images, captions, lengths, return_embeddings=True)
     if gather is not None:
         img, txt = gather(img), gather(txt)
@@ -118,3 +121,51 @@ def classifier_step(model, optimizer, batch):
     loss.backward()
     optimizer.step()
     return loss
+
+
+# ---- CUDA-graph capture of the whole optimisation step ----------------------------------
+
+class GraphedRetrievalStep:
+    """Captures zero_grad + forward + loss + backward (+ gradient all-reduce) + AdamW into ONE CUDA
+    graph.  The small-shape configs are launch-bound (~1000 kernels per step, most a few
+    microseconds); the hot path was written without host synchronisation (thresholds, alpha and the
+    validation flags stay on the device) precisely so that it can be captured.  Replays re-run the
+    per-layer quantization kernels on the live weights, exactly like the eager step."""
+
+    def __init__(self, model, manager, optimizer, example_batch, gather=None, grad_sync=None, warmup=3, prepare=None):
+        self.model = model
+        self.static_batch = tuple(t.clone() for t in example_batch)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                retrieval_step(model, manager, optimizer, self.static_batch, gather, grad_sync, prepare)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        if grad_sync is None:
+            optimizer.zero_grad(set_to_none=True)
+        try:
+            import atq._native as nv
+            k0 = nv.kernel_launch_count()
+        except ImportError:
+            nv, k0 = None, 0
+        with torch.cuda.graph(self.graph):
+            self.static_loss = retrieval_step(model, manager, optimizer, self.static_batch, gather, grad_sync, prepare)
+        # kernels of libatq_sm100 recorded in the graph (each replay launches them again)
+        self.own_kernels_per_replay = (nv.kernel_launch_count() - k0) if nv is not None else 0
+
+    def __call__(self, batch):
+        for dst, src in zip(self.static_batch, batch):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss
+
+    def release(self):
+        """Back to eager execution: graph replays update the weights without bumping tensor versions,
+        so the layers' operand caches must be dropped."""
+        for m in self.model.modules():
+            ops = getattr(m, "_ops", None)
+            if ops is not None:
+                ops.key = None
