@@ -374,14 +374,15 @@ def run_ours(args, cfg):
                     "ms_per_step": round(ms_e2e / args.steps, 4)},
             "gpu_launches": int(launches), "clocks": clocks, "final_loss": round(final_loss, 5)}
 
+    # ---- roofline of the dominant kernel of THIS library inside the step (separate untimed pass;
+    # every rank runs it because the step contains collectives, rank 0 reports)
+    if gstep is not None:
+        gstep.release()
+    prof = CallProfiler()
+    with prof:
+        for i in range(2):
+            eager_step(resident[i % pool])
     if rank == 0:
-        # ---- roofline of the dominant kernel of THIS library inside the step (separate untimed pass)
-        if gstep is not None:
-            gstep.release()
-        prof = CallProfiler()
-        with prof:
-            for i in range(2):
-                eager_step(resident[i % pool])
         summ = prof.summary()
         own_ms = sum(d["ms"] for d in summ.values()) / 2
         top = max(summ.items(), key=lambda kv: kv[1]["ms"]) if summ else None
@@ -414,8 +415,20 @@ def run_ours(args, cfg):
                                               f"{round(s_per, 3)} s/step"}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # tear down in a fixed order (captured NCCL kernels first); a watchdog guarantees the process
+        # exits even if communicator destruction stalls
+        sys.stdout.flush()
+        threading.Timer(30.0, lambda: os._exit(0)).start()
+        torch.cuda.synchronize()
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        if gstep is not None:
+            gstep.graph.reset()
+            del gstep
+        torch.cuda.synchronize()
+        try:
+            torch.distributed.destroy_process_group()
+        finally:
+            os._exit(0)
 
 
 def main():
