@@ -49,6 +49,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -140,17 +143,25 @@ struct GemmParams {
   float* partials;        // [gridDim.x * gridDim.y], nullable
 };
 
+constexpr int kStagingBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp [32][33] fp32 transposition buffers
+
 template <int NUM_A, int NUM_B, int BLOCK_N>
 struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = NUM_A * kABytes + NUM_B * kBBytes;
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
+  static_assert(kTmemCols <= 512, "TMEM has 512 columns");
 };
 
+// Persistent, warp-specialised: one CTA per SM walks output tiles t = blockIdx.x + i*gridDim.x
+// (column tile fastest, so the CTAs working at the same time share A tiles through L2 and the
+// whole B operand stays L2-resident).  The accumulator is double-buffered in TMEM: the MMA warp
+// starts tile i+1 while the epilogue warps drain tile i.
 template <int NUM_A, int NUM_B, int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     tgemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -162,19 +173,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bars = smem_base + kStages * Cfg::kStageBytes;  // 8-byte aligned
+  constexpr int kBarOff = kStages * Cfg::kStageBytes + kStagingBytes;
+  const uint32_t bars = smem_base + kBarOff;  // 8-byte aligned
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
-  const uint32_t tmem_full_bar = bars + 8u * (2 * kStages);
-  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 1);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 1));
-  float* s_part = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 2));
+  auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+  auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + kBarOff + 8 * (2 * kStages + 4));
+  float* s_part = reinterpret_cast<float*>(smem_gen + kBarOff + 8 * (2 * kStages + 5));
 
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int64_t n0 = (int64_t)blockIdx.x * BLOCK_N;  // column tile (x fastest: CTAs of one wave share A tiles)
-  const int64_t m0 = (int64_t)blockIdx.y * BLOCK_M;
   const int num_kb = (int)((p.kdim + BLOCK_K - 1) / BLOCK_K);
+  const int tiles_n = (int)((p.cols + BLOCK_N - 1) / BLOCK_N);
+  const int tiles_m = (int)((p.rows + BLOCK_M - 1) / BLOCK_M);
+  const int num_tiles = tiles_n * tiles_m;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -185,33 +199,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tmem_full_bar(a), 1);
+      mbar_init(tmem_empty_bar(a), 4);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc<BLOCK_N>(tmem_slot);
+    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_acc = *tmem_slot_gen;
+  const uint32_t tmem_base = *tmem_slot_gen;
 
   if (warp_idx == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-        const int32_t kc = kb * BLOCK_K;
-        tma_load_2d(sa, &map_a_hi, kc, (int32_t)m0, full_bar(stage));
-        if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes, &map_a_lo, kc, (int32_t)m0, full_bar(stage));
-        const uint32_t sb = sa + NUM_A * Cfg::kABytes;
-        tma_load_2d(sb, &map_b_hi, kc, (int32_t)n0, full_bar(stage));
-        if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, (int32_t)n0, full_bar(stage));
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int32_t n0 = (t % tiles_n) * BLOCK_N;
+        const int32_t m0 = (t / tiles_n) * BLOCK_M;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          const int32_t kc = kb * BLOCK_K;
+          tma_load_2d(sa, &map_a_hi, kc, m0, full_bar(stage));
+          if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes, &map_a_lo, kc, m0, full_bar(stage));
+          const uint32_t sb = sa + NUM_A * Cfg::kABytes;
+          tma_load_2d(sb, &map_b_hi, kc, n0, full_bar(stage));
+          if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, n0, full_bar(stage));
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp_idx == 1) {
@@ -220,82 +241,109 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       constexpr uint32_t idesc = make_idesc<BLOCK_N>();
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t accumulate = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int a = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tmem_empty_bar(a), aphase ^ 1u);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
-        const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-        const uint32_t sb = sa + NUM_A * Cfg::kABytes;
-        const uint64_t da_hi = make_smem_desc_kmajor_sw128(sa);
-        const uint64_t da_lo = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
-        const uint64_t db_hi = make_smem_desc_kmajor_sw128(sb);
-        const uint64_t db_lo = make_smem_desc_kmajor_sw128(sb + Cfg::kBBytes);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N);
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sb = sa + NUM_A * Cfg::kABytes;
+          const uint64_t da_hi = make_smem_desc_kmajor_sw128(sa);
+          const uint64_t da_lo = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
+          const uint64_t db_hi = make_smem_desc_kmajor_sw128(sb);
+          const uint64_t db_lo = make_smem_desc_kmajor_sw128(sb + Cfg::kBBytes);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // 32 B per K step, in 16 B units
-          umma_bf16(tmem_acc, da_hi + koff, db_hi + koff, idesc, accumulate);
-          accumulate = 1;
-          if (NUM_A == 2) umma_bf16(tmem_acc, da_lo + koff, db_hi + koff, idesc, 1u);
-          if (NUM_B == 2) umma_bf16(tmem_acc, da_hi + koff, db_lo + koff, idesc, 1u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // 32 B per K step, in 16 B units
+            umma_bf16(tmem_acc, da_hi + koff, db_hi + koff, idesc, accumulate);
+            accumulate = 1;
+            if (NUM_A == 2) umma_bf16(tmem_acc, da_lo + koff, db_hi + koff, idesc, 1u);
+            if (NUM_B == 2) umma_bf16(tmem_acc, da_hi + koff, db_lo + koff, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above retire
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        umma_commit(tmem_full_bar(a));  // accumulator of this tile complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ================= epilogue warps 2..5 =================
     // TMEM gives each thread one accumulator ROW (32 columns per tcgen05.ld).  Rows are staged
-    // through shared memory (the pipeline stages are idle once tmem_full fires) so that every
-    // global access below is a warp-wide 128-byte row segment: lane = column.
+    // through a private shared-memory buffer so that every global access below is a warp-wide
+    // 128-byte row segment: lane = column.
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    float* stg = reinterpret_cast<float*>(smem_gen) + (warp_idx - 2) * (32 * 33);  // [32][33] per warp
-    const int64_t r_base = m0 + quarter * 32;
+    float* stg = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes) + (warp_idx - 2) * (32 * 33);
     const float scale = (EPI == EPI_LINEAR && p.scale != nullptr) ? __ldg(p.scale) : 1.f;
     float partial = 0.f;
-#pragma unroll 1
-    for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-      const int64_t c0 = n0 + ch * 32;
-      if (c0 >= p.cols || r_base >= p.rows) break;  // warp-uniform
-      uint32_t acc[32];
-      tmem_ld_32x32b_x32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * 32), acc);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(acc[j]);  // bank (lane+j)%32: conflict-free
-      __syncwarp();
-      const int64_t c = c0 + lane;
-      const bool col_ok = c < p.cols;
-      const int rows_here = (int)((p.rows - r_base) < 32 ? (p.rows - r_base) : 32);
-      if constexpr (EPI == EPI_LINEAR) {
-        const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + c) : 0.f;
-        if (col_ok) {
-#pragma unroll 8
-          for (int rr = 0; rr < rows_here; ++rr) {
-            const int64_t r = r_base + rr;
-            float v = stg[rr * 33 + lane];
-            if (p.dot_ref != nullptr) partial += v * __ldg(p.dot_ref + r * p.dot_ref_pitch + c);
-            p.out[r * p.out_pitch + c] = v * scale + bias;
-          }
-        }
-      } else {
-        if (col_ok) {
-#pragma unroll 8
-          for (int rr = 0; rr < rows_here; ++rr) {
-            const int64_t r = r_base + rr;
-            const int64_t i = r * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
-            const float g = stg[rr * 33 + lane];
-            const float mk = p.mask ? __ldg(p.mask + i) : 1.f;
-            if (p.tern != nullptr) {
-              const uint32_t code = ((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u;
-              partial += g * ((float)code - 1.f) * (1.f - mk);
-            }
-            p.out[r * p.out_pitch + c] = g * mk;
-          }
-        }
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int64_t n0 = (int64_t)(t % tiles_n) * BLOCK_N;
+      const int64_t m0 = (int64_t)(t / tiles_n) * BLOCK_M;
+      mbar_wait(tmem_full_bar(a), aphase);
+      tcgen05_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
+      const int64_t r_base = m0 + quarter * 32;
+      // number of 32-column chunks of this tile that hold real output (warp-uniform)
+      int nch = (int)((p.cols - n0 + 31) / 32);
+      if (nch > BLOCK_N / 32) nch = BLOCK_N / 32;
+      if (r_base >= p.rows) nch = 0;
+      if (nch == 0) {
+        tcgen05_fence_before();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(a));
       }
-      __syncwarp();  // staging buffer reuse + reconverge before the next warp-aligned tcgen05.ld
+#pragma unroll 1
+      for (int ch = 0; ch < nch; ++ch) {
+        const int64_t c0 = n0 + ch * 32;
+        uint32_t acc[32];
+        tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(ch * 32), acc);
+        tmem_ld_wait();
+        if (ch == nch - 1) {  // everything this warp needs has left TMEM: hand the buffer back
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(acc[j]);  // bank (lane+j)%32: conflict-free
+        __syncwarp();
+        const int64_t c = c0 + lane;
+        const bool col_ok = c < p.cols;
+        const int rows_here = (int)((p.rows - r_base) < 32 ? (p.rows - r_base) : 32);
+        if constexpr (EPI == EPI_LINEAR) {
+          const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + c) : 0.f;
+          if (col_ok) {
+#pragma unroll 8
+            for (int rr = 0; rr < rows_here; ++rr) {
+              const int64_t r = r_base + rr;
+              float v = stg[rr * 33 + lane];
+              if (p.dot_ref != nullptr) partial += v * __ldg(p.dot_ref + r * p.dot_ref_pitch + c);
+              p.out[r * p.out_pitch + c] = v * scale + bias;
+            }
+          }
+        } else {
+          if (col_ok) {
+#pragma unroll 8
+            for (int rr = 0; rr < rows_here; ++rr) {
+              const int64_t r = r_base + rr;
+              const int64_t i = r * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
+              const float g = stg[rr * 33 + lane];
+              const float mk = p.mask ? __ldg(p.mask + i) : 1.f;
+              if (p.tern != nullptr) {
+                const uint32_t code = ((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u;
+                partial += g * ((float)code - 1.f) * (1.f - mk);
+              }
+              p.out[r * p.out_pitch + c] = g * mk;
+            }
+          }
+        }
+        __syncwarp();  // staging buffer reuse + reconverge before the next warp-aligned tcgen05.ld
+      }
     }
     if (p.partials != nullptr) {
       partial = warp_sum(partial);
@@ -306,10 +354,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   __syncthreads();
   if (warp_idx == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<BLOCK_N>(tmem_acc);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
   if (p.partials != nullptr && threadIdx.x == 0) {
-    p.partials[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+    p.partials[blockIdx.x] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
   }
 }
 
@@ -368,7 +416,7 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
 }
 
 template <int NUM_A, int NUM_B, int BLOCK_N, int EPI>
-static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream) {
+static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
   using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
@@ -391,11 +439,14 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
     }
     attr_done = true;
   }
-  dim3 grid((unsigned)((p.cols + BLOCK_N - 1) / BLOCK_N), (unsigned)((p.rows + BLOCK_M - 1) / BLOCK_M));
-  if (grid.y > 65535u) {
-    set_error("tgemm: rows too large for one launch (%lld)", (long long)p.rows);
+  const int64_t tiles = ((p.cols + BLOCK_N - 1) / BLOCK_N) * ((p.rows + BLOCK_M - 1) / BLOCK_M);
+  if (tiles > 0x7fffffff) {
+    set_error("tgemm: too many tiles (%lld)", (long long)tiles);
     return ATQ_EINVAL;
   }
+  const int sms = sm_count(dev);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  *grid_used = grid;
   kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -407,12 +458,12 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
 }
 
 template <int EPI>
-static int dispatch(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* bn_used) {
+static int dispatch(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
   const bool a2 = a->lo != nullptr, b2 = b->lo != nullptr;
   // tile width: 256 columns when the pipeline still has >= 3 stages, else 128; narrow outputs use 64/128
   const bool narrow = p.cols <= 64;
   const bool mid = p.cols <= 128;
-#define ATQ_GO(NA, NB, BN) do { *bn_used = BN; return launch_cfg<NA, NB, BN, EPI>(a, b, p, stream); } while (0)
+#define ATQ_GO(NA, NB, BN) return launch_cfg<NA, NB, BN, EPI>(a, b, p, stream, grid_used)
   if (narrow) {
     if (a2 && b2) ATQ_GO(2, 2, 64);
     if (a2) ATQ_GO(2, 1, 64);
@@ -478,11 +529,10 @@ int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf
   p.scale = scale; p.bias = bias;
   p.dot_ref = dot_ref; p.dot_ref_pitch = dot_ref_pitch;
   p.partials = dot_out ? (float*)ws : nullptr;
-  int bn = 0;
-  if ((r = dispatch<EPI_LINEAR>(a, b, p, stream, &bn)) != ATQ_OK) return r;
+  int grid = 0;
+  if ((r = dispatch<EPI_LINEAR>(a, b, p, stream, &grid)) != ATQ_OK) return r;
   if (dot_out) {
-    int64_t tiles = ((cols + bn - 1) / bn) * ((rows + BLOCK_M - 1) / BLOCK_M);
-    reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, tiles, dot_out);
+    reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, grid, dot_out);
     ATQ_LAUNCH_CHECK();
   }
   return ATQ_OK;
@@ -525,11 +575,10 @@ int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, i
   p.out = dw; p.out_pitch = dw_pitch;
   p.mask = mask; p.tern = packed_t;
   p.partials = dalpha_out ? (float*)ws : nullptr;
-  int bn = 0;
-  if ((r = dispatch<EPI_MASKED>(dy_t, x_t, p, stream, &bn)) != ATQ_OK) return r;
+  int grid = 0;
+  if ((r = dispatch<EPI_MASKED>(dy_t, x_t, p, stream, &grid)) != ATQ_OK) return r;
   if (dalpha_out) {
-    int64_t tiles = ((in_features + bn - 1) / bn) * ((out_features + BLOCK_M - 1) / BLOCK_M);
-    reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, tiles, dalpha_out);
+    reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, grid, dalpha_out);
     ATQ_LAUNCH_CHECK();
   }
   return ATQ_OK;
