@@ -207,3 +207,39 @@ def test_routing(golden, policy):
     xg = xr.to(DEV).requires_grad_(True)
     atq.SelectiveGradientRouting.apply(xg, 0.05, 0.3).backward(gr.to(DEV))
     assert np.array_equal(xg.grad.cpu().numpy(), O.routing_backward(xr.numpy(), gr.numpy(), 0.3))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "normal", "ties", "wide", "constant", "two_level"])
+def test_sampled_select_large_layers_bit_exact(kind):
+    """n >= 32M takes the sampling front-end (bracket + one filter pass + candidate select); massive ties
+    and adversarial layouts must fall back to the full radix select and stay exact."""
+    n = (1 << 25) + 3
+    g = torch.Generator().manual_seed(11)
+    if kind == "constant":
+        w = torch.full((n,), 0.25)
+    elif kind == "two_level":  # sample positions see only small values, the rest is large
+        w = torch.rand(n, generator=g) + 1.0
+        stride = n // 8192
+        w[stride // 2:: stride] = 1e-3
+    else:
+        w = _weights((n,), 17, kind)
+    wg = w.to(DEV)
+    a = np.abs(w.numpy())
+    for s in (0.3, 0.05, 0.97, 1e-6):
+        k = int(s * n)
+        if k == 0:
+            continue
+        want = np.float32(np.partition(a, k)[k])
+        got = eng.adaptive_threshold(wg, s)
+        assert np.float32(got.item()).tobytes() == want.tobytes(), (kind, s)
+    # routing percentile goes through the same kernel (k-1 indexing)
+    got = eng.select_kth_abs(wg, 0)
+    assert np.float32(got.item()).tobytes() == np.float32(a.min()).tobytes()
+    got = eng.select_kth_abs(wg, n - 1)
+    assert np.float32(got.item()).tobytes() == np.float32(a.max()).tobytes()
+    # batched entry point mixes small and large layers
+    small = _weights((192, 192), 3, "uniform").to(DEV)
+    thr = eng.adaptive_threshold_batched([small, wg, small], [0.3, 0.3, 0.1])
+    assert float(thr[1]) == float(eng.adaptive_threshold(wg, 0.3))
+    assert float(thr[0]) == float(eng.adaptive_threshold(small, 0.3))
+    assert float(thr[2]) == float(eng.adaptive_threshold(small, 0.1))
