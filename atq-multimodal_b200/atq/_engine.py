@@ -217,6 +217,25 @@ def tgemm(a, b, rows: int, cols: int, kdim: int, scale=None, bias=None, dot_ref=
     return out, dot_out
 
 
+def tgemm_packed(a, packed_b: torch.Tensor, rows: int, cols: int, kdim: int, scale=None, bias=None, dot_ref=None):
+    """out[rows, cols] = scale * (A . T^T) + bias with T given as 2-bit codec bytes [cols, kdim/4]
+    (kdim % 64 == 0): the packed weights are expanded to bf16 tiles in shared memory by the GEMM."""
+    hi = a[0]
+    dev = nv.device_index(hi)
+    out = torch.empty((rows, cols), dtype=torch.float32, device=hi.device)
+    oa = nv.operand(*a)
+    dot_out = torch.empty(1, dtype=torch.float32, device=hi.device) if dot_ref is not None else None
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_tgemm(rows, cols) if dot_ref is not None else 0, hi.device)
+    nv.call("atq_tgemm_packed", dev, rows, cols, kdim, ctypes.byref(oa), packed_b.data_ptr(), nv.ptr(scale), nv.ptr(bias),
+            out.data_ptr(), cols, nv.ptr(dot_ref), 0 if dot_ref is None else dot_ref.stride(0), nv.ptr(dot_out),
+            ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+    return out, dot_out
+
+
+def packed_gemm_ok(kdim: int, packed: torch.Tensor) -> bool:
+    return kdim % 64 == 0 and packed is not None and packed.data_ptr() % 16 == 0
+
+
 def tgemm_dw_masked(dy_t, x_t, m_out: int, k_in: int, n_tok: int, mask=None, packed=None):
     hi = dy_t[0]
     dev = nv.device_index(hi)
@@ -235,14 +254,15 @@ def tgemm_dw_masked(dy_t, x_t, m_out: int, k_in: int, n_tok: int, mask=None, pac
 # ---------------------------------------------------------------------------------------
 
 class LayerOperands:
-    __slots__ = ("key", "thr", "packed", "w", "w_t", "packed_flat_ok")
+    __slots__ = ("key", "thr", "packed", "packed_t", "w", "w_t")
 
     def __init__(self):
         self.key = None
         self.thr = None
-        self.packed = None
-        self.w = None      # (hi, lo|None, pitch)   [M, pitch]  forward B operand
-        self.w_t = None    # (hi, lo|None, pitch_t) [K, pitch_t] dX B operand
+        self.packed = None    # 2-bit codec bytes of T, public layout [M*K/4]
+        self.packed_t = None  # codec bytes of T^T [K, M/4] (TernaryLinear, M % 64 == 0)
+        self.w = None      # (hi, lo|None, pitch)   [M, pitch]  forward B operand (None when packed is used)
+        self.w_t = None    # (hi, lo|None, pitch_t) [K, pitch_t] dX B operand (None when packed_t is used)
 
 
 def _key(weight, alpha, mask, sparsity_target, threshold_factor):
@@ -267,19 +287,28 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
         thr = adaptive_threshold(w, sparsity_target, threshold_factor)
     pitch, pitch_t = nv.round_up(K, 8), nv.round_up(M, 8)
     n = M * K
-    want_lo = _use_lo() and mask is not None
     bf = torch.bfloat16
-    hi = torch.empty((M, pitch), dtype=bf, device=w.device)
-    hi_t = torch.empty((K, pitch_t), dtype=bf, device=w.device)
-    lo = torch.empty((M, pitch), dtype=bf, device=w.device) if want_lo else None
-    lo_t = torch.empty((K, pitch_t), dtype=bf, device=w.device) if want_lo else None
     packed = torch.empty((n + 3) // 4, dtype=torch.uint8, device=w.device)
     flat_ok = (K % 4 == 0)
     st = nv.stream_ptr(dev)
+    packed_t = None
     if mask is None:
+        # TernaryLinear: the GEMMs read the 2-bit codec bytes directly whenever the contraction
+        # dimension allows 16-byte codec rows per k-block; bf16 copies only for odd shapes
+        fwd_packed, dx_packed = (K % 64 == 0), (M % 64 == 0)
+        hi = None if fwd_packed else torch.empty((M, pitch), dtype=bf, device=w.device)
+        hi_t = None if dx_packed else torch.empty((K, pitch_t), dtype=bf, device=w.device)
+        if dx_packed:
+            packed_t = torch.empty(n // 4, dtype=torch.uint8, device=w.device)
+        lo = lo_t = None
         nv.call("atq_build_ternary_operands", dev, w.data_ptr(), M, K, thr.data_ptr(),
-                packed.data_ptr() if flat_ok else None, hi.data_ptr(), pitch, hi_t.data_ptr(), pitch_t, None, st)
+                packed.data_ptr() if flat_ok else None, nv.ptr(packed_t), nv.ptr(hi), pitch, nv.ptr(hi_t), pitch_t, None, st)
     else:
+        want_lo = _use_lo()
+        hi = torch.empty((M, pitch), dtype=bf, device=w.device)
+        hi_t = torch.empty((K, pitch_t), dtype=bf, device=w.device)
+        lo = torch.empty((M, pitch), dtype=bf, device=w.device) if want_lo else None
+        lo_t = torch.empty((K, pitch_t), dtype=bf, device=w.device) if want_lo else None
         mk = nv.require_f32(mask, "precision_mask")
         al = nv.require_f32(alpha.detach(), "alpha")
         nv.call("atq_build_mixed_operands", dev, w.data_ptr(), mk.data_ptr(), M, K, thr.data_ptr(), al.data_ptr(),
@@ -287,8 +316,9 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
                 nv.ptr(lo_t), pitch_t, st)
     if not flat_ok:  # rows of the flat codec do not start on byte boundaries
         nv.call("atq_ternarize_pack2", dev, w.data_ptr(), n, thr.data_ptr(), packed.data_ptr(), None, st)
-    cache.key, cache.thr, cache.packed = key, thr, packed
-    cache.w, cache.w_t = (hi, lo, pitch), (hi_t, lo_t, pitch_t)
+    cache.key, cache.thr, cache.packed, cache.packed_t = key, thr, packed, packed_t
+    cache.w = None if hi is None else (hi, lo, pitch)
+    cache.w_t = None if hi_t is None else (hi_t, lo_t, pitch_t)
     return cache
 
 
@@ -335,9 +365,13 @@ class _TernaryLinearFn(torch.autograd.Function):
             y = x2.new_zeros((0, M))
         else:
             xa = split_bf16(x2, _use_lo())
-            y, _ = tgemm(xa, ops.w, N, M, K, scale=al, bias=None if bias is None else bias.detach())
+            b_ = None if bias is None else bias.detach()
+            if ops.w is None:   # packed 2-bit weights, unpacked to bf16 tiles inside the GEMM
+                y, _ = tgemm_packed(xa, ops.packed, N, M, K, scale=al, bias=b_)
+            else:
+                y, _ = tgemm(xa, ops.w, N, M, K, scale=al, bias=b_)
         ctx.save_for_backward(x2, al)
-        ctx.ops_w_t = ops.w_t
+        ctx.ops_w_t, ctx.packed_t = ops.w_t, ops.packed_t
         ctx.has_bias = bias is not None
         ctx.wshape = (M, K)
         ctx.xshape = x.shape
@@ -356,7 +390,10 @@ class _TernaryLinearFn(torch.autograd.Function):
             return (gy.new_zeros(ctx.xshape), None, al.new_zeros(1), g2.new_zeros(M) if ctx.has_bias else None, None)
         ga = split_bf16(g2, _use_lo())
         # dX = alpha * (dY . T);  d(alpha) = sum((dY . T) .* X) fused in the same epilogue
-        dx, dalpha = tgemm(ga, ctx.ops_w_t, N, K, M, scale=al, dot_ref=x2)
+        if ctx.ops_w_t is None:
+            dx, dalpha = tgemm_packed(ga, ctx.packed_t, N, K, M, scale=al, dot_ref=x2)
+        else:
+            dx, dalpha = tgemm(ga, ctx.ops_w_t, N, K, M, scale=al, dot_ref=x2)
         dbias = colsum(g2) if ctx.has_bias else None
         dw = None
         if ctx.ste:  # opt-in straight-through estimator: dW = G

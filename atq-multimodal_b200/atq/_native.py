@@ -21,7 +21,7 @@ if not os.path.exists(_LIB_PATH):
         "(or `make -C atq-multimodal_b200/csrc`). The atq package has no CPU or eager fallback.")
 _lib = ctypes.CDLL(_LIB_PATH)
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class BF16Operand(Structure):
@@ -54,12 +54,14 @@ _SIGS = {
     "atq_route_mask_mul": (c_int, [c_int, _P, _P, _P, c_int64, _P, _P]),
     "atq_split_bf16": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
     "atq_split_bf16_t": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P]),
-    "atq_build_ternary_operands": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int64, _P, _P]),
+    "atq_build_ternary_operands": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P]),
     "atq_build_mixed_operands": (c_int, [c_int, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P,
                                          c_int64, _P]),
     "atq_workspace_bytes_tgemm": (c_size_t, [c_int64, c_int64]),
     "atq_tgemm": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P, _P,
                           c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
+    "atq_tgemm_packed": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), _P, _P, _P, _P,
+                                 c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
     "atq_tgemm_fwd": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P,
                               _P, c_int64, _P, c_size_t, _P]),
     "atq_tgemm_dx": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P,

@@ -60,13 +60,18 @@ class TernaryBitPacking:
         x = nv.require_f32(input_tensor, "input_tensor")
         if x.shape[-1] != K:
             raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied ({tuple(x.shape)} and {K}x{M})")
-        tb = eng.unpack2(packed, M * K, torch.bfloat16).view(M, K)
-        pitch = nv.round_up(K, 8)
-        if pitch != K:
-            tb = torch.nn.functional.pad(tb, (0, pitch - K))
         x2 = x.reshape(-1, K)
         if x2.shape[0] == 0:
             return x.new_zeros(*x.shape[:-1], M) * alpha
         xa = eng.split_bf16(x2, eng.get_gemm_mode() == "parity")
-        y, _ = eng.tgemm(xa, (tb, None, pitch), x2.shape[0], M, K)
+        packed = packed.contiguous()
+        if eng.packed_gemm_ok(K, packed):
+            # the GEMM reads the codec bytes and expands them in shared memory
+            y, _ = eng.tgemm_packed(xa, packed, x2.shape[0], M, K)
+        else:
+            tb = eng.unpack2(packed, M * K, torch.bfloat16).view(M, K)
+            pitch = nv.round_up(K, 8)
+            if pitch != K:
+                tb = torch.nn.functional.pad(tb, (0, pitch - K))
+            y, _ = eng.tgemm(xa, (tb, None, pitch), x2.shape[0], M, K)
         return y.reshape(*x.shape[:-1], M) * alpha

@@ -23,6 +23,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 192;
+// packed-B kernels add BLOCK_N/32 converter warps (one B-tile row per thread)
+constexpr int gemm_threads(bool packed, int block_n) { return kGemmThreads + (packed ? block_n : 0); }
 constexpr int kSmemBudget = 227 * 1024 - 2048;
 
 // ------------------------------------------------------------------------------------------
@@ -126,6 +128,40 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
 }
 
 // ------------------------------------------------------------------------------------------
+// 2-bit codec -> bf16 in registers.  One 32-bit word holds 16 codes (code i at bits 2i..2i+1,
+// value = code - 1).  Codes i and i+8 are 16 bits apart, so a single AND/OR drops both into the
+// low mantissa bits of a bf16x2 whose exponent is 2^7: (0x4300 | c << sh) == 128 + c * 2^sh,
+// and one bf16x2 FMA maps that to c - 1 exactly.  A byte permute restores K order.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ void unpack16_to_bf16(uint32_t w, uint4& lo8, uint4& hi8) {
+  constexpr uint32_t kMagic = 0x43004300u;  // 128.0, 128.0
+  constexpr uint32_t kS0 = 0x3F803F80u, kB0 = 0xC301C301u;  // * 1      - 129
+  constexpr uint32_t kS2 = 0x3E803E80u, kB2 = 0xC204C204u;  // * 0.25   - 33
+  constexpr uint32_t kS4 = 0x3D803D80u, kB4 = 0xC110C110u;  // * 0.0625 - 9
+  const uint32_t x1 = w >> 6, x2 = w >> 12;
+  const uint32_t a0 = bf16x2_fma((w & 0x00030003u) | kMagic, kS0, kB0);   // codes 0, 8
+  const uint32_t a1 = bf16x2_fma((w & 0x000C000Cu) | kMagic, kS2, kB2);   // codes 1, 9
+  const uint32_t a2 = bf16x2_fma((w & 0x00300030u) | kMagic, kS4, kB4);   // codes 2, 10
+  const uint32_t a3 = bf16x2_fma((x1 & 0x00030003u) | kMagic, kS0, kB0);  // codes 3, 11
+  const uint32_t a4 = bf16x2_fma((x1 & 0x000C000Cu) | kMagic, kS2, kB2);  // codes 4, 12
+  const uint32_t a5 = bf16x2_fma((x1 & 0x00300030u) | kMagic, kS4, kB4);  // codes 5, 13
+  const uint32_t a6 = bf16x2_fma((x2 & 0x00030003u) | kMagic, kS0, kB0);  // codes 6, 14
+  const uint32_t a7 = bf16x2_fma((x2 & 0x000C000Cu) | kMagic, kS2, kB2);  // codes 7, 15
+  lo8 = make_uint4(__byte_perm(a0, a1, 0x5410), __byte_perm(a2, a3, 0x5410), __byte_perm(a4, a5, 0x5410),
+                   __byte_perm(a6, a7, 0x5410));  // values 0..7
+  hi8 = make_uint4(__byte_perm(a0, a1, 0x7632), __byte_perm(a2, a3, 0x7632), __byte_perm(a4, a5, 0x7632),
+                   __byte_perm(a6, a7, 0x7632));  // values 8..15
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
 enum { EPI_LINEAR = 0, EPI_MASKED = 1 };
@@ -140,7 +176,9 @@ struct GemmParams {
   int64_t dot_ref_pitch;
   const float* mask;      // fp32 [rows, cols] contiguous, nullable (MASKED): out = acc * mask
   const uint8_t* tern;    // 2-bit codec bytes of T [rows*cols], nullable (MASKED): partial += acc*T*(1-mask)
-  float* partials;        // [gridDim.x * gridDim.y], nullable
+  float* partials;        // [gridDim.x], nullable
+  const uint8_t* b_packed;  // B_PACKED kernels: 2-bit codec bytes of T, [cols, kdim/4] row-major
+  int64_t b_packed_pitch;   // bytes per row (= kdim / 4)
 };
 
 constexpr int kStagingBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp [32][33] fp32 transposition buffers
@@ -162,8 +200,8 @@ struct GemmCfg {
 // (column tile fastest, so the CTAs working at the same time share A tiles through L2 and the
 // whole B operand stays L2-resident).  The accumulator is double-buffered in TMEM: the MMA warp
 // starts tile i+1 while the epilogue warps drain tile i.
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false>
+__global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     tgemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const GemmParams p) {
@@ -192,11 +230,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
-    tma_prefetch_desc(&map_b_hi);
+    if (!B_PACKED) tma_prefetch_desc(&map_b_hi);
     if (NUM_A == 2) tma_prefetch_desc(&map_a_lo);
     if (NUM_B == 2) tma_prefetch_desc(&map_b_lo);
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), B_PACKED ? 1 + BLOCK_N / 32 : 1);  // TMA expect-tx arrival (+ one per converter warp)
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -224,13 +262,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+          mbar_expect_tx(full_bar(stage), B_PACKED ? NUM_A * Cfg::kABytes : Cfg::kStageBytes);
           const int32_t kc = kb * BLOCK_K;
           tma_load_2d(sa, &map_a_hi, kc, m0, full_bar(stage));
           if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes, &map_a_lo, kc, m0, full_bar(stage));
-          const uint32_t sb = sa + NUM_A * Cfg::kABytes;
-          tma_load_2d(sb, &map_b_hi, kc, n0, full_bar(stage));
-          if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, n0, full_bar(stage));
+          if constexpr (!B_PACKED) {
+            const uint32_t sb = sa + NUM_A * Cfg::kABytes;
+            tma_load_2d(sb, &map_b_hi, kc, n0, full_bar(stage));
+            if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, n0, full_bar(stage));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -272,6 +312,59 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         umma_commit(tmem_full_bar(a));  // accumulator of this tile complete
       }
     }
+  } else if (B_PACKED && warp_idx >= 6) {
+    // ================= converter warps 6..: packed 2-bit T -> bf16 B tile in shared memory =================
+    // Each thread owns one row of the tile: one 16-byte load (64 codes) per
+    // k-block, expanded to 128 bytes of bf16 and stored with the SWIZZLE_128B pattern the UMMA
+    // descriptor expects (16-byte chunk c of row r lives at chunk c ^ (r & 7)).
+    if constexpr (B_PACKED) {
+    constexpr int kRows = 1;
+    const int ct = threadIdx.x - 6 * 32;  // 0..BLOCK_N-1
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int64_t n0 = (int64_t)(t % tiles_n) * BLOCK_N;
+      uint4 cur[kRows];
+      auto load_row = [&](int i, int kb) -> uint4 {
+        const int64_t row = n0 + ct + i * BLOCK_N;
+        if (row < p.cols) return __ldg(reinterpret_cast<const uint4*>(p.b_packed + row * p.b_packed_pitch + (int64_t)kb * 16));
+        return make_uint4(0x55555555u, 0x55555555u, 0x55555555u, 0x55555555u);  // code 1 = 0.0
+      };
+#pragma unroll
+      for (int i = 0; i < kRows; ++i) cur[i] = load_row(i, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        uint4 nxt[kRows];
+        if (kb + 1 < num_kb) {
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) nxt[i] = load_row(i, kb + 1);  // in flight while this block converts
+        }
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sb = smem_base + stage * Cfg::kStageBytes + NUM_A * Cfg::kABytes;
+#pragma unroll
+        for (int i = 0; i < kRows; ++i) {
+          const int r = ct + i * BLOCK_N;
+          const uint32_t row_addr = sb + (uint32_t)r * 128u;
+          const uint32_t sw = (uint32_t)(r & 7);
+          const uint32_t words[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 lo8, hi8;
+            unpack16_to_bf16(words[q], lo8, hi8);
+            st_shared_v4(row_addr + (((uint32_t)(2 * q) ^ sw) << 4), lo8);
+            st_shared_v4(row_addr + (((uint32_t)(2 * q + 1) ^ sw) << 4), hi8);
+          }
+        }
+        fence_proxy_async();  // make these generic-proxy stores visible to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_bar(stage));
+        if (kb + 1 < num_kb) {
+#pragma unroll
+          for (int i = 0; i < kRows; ++i) cur[i] = nxt[i];
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    }  // if constexpr (B_PACKED)
   } else {
     // ================= epilogue warps 2..5 =================
     // TMEM gives each thread one accumulator ROW (32 columns per tcgen05.ld).  Rows are staged
@@ -415,18 +508,22 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
   return ATQ_OK;
 }
 
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI>
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false>
 static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
   using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   if ((r = make_map(&ma_hi, a->hi, p.rows, p.kdim, a->pitch, BLOCK_M)) != ATQ_OK) return r;
-  if ((r = make_map(&mb_hi, b->hi, p.cols, p.kdim, b->pitch, BLOCK_N)) != ATQ_OK) return r;
+  if constexpr (!B_PACKED) {
+    if ((r = make_map(&mb_hi, b->hi, p.cols, p.kdim, b->pitch, BLOCK_N)) != ATQ_OK) return r;
+  } else {
+    mb_hi = ma_hi;  // unused by the packed-B kernel
+  }
   ma_lo = ma_hi;
   mb_lo = mb_hi;
   if (NUM_A == 2 && (r = make_map(&ma_lo, a->lo, p.rows, p.kdim, a->pitch, BLOCK_M)) != ATQ_OK) return r;
   if (NUM_B == 2 && (r = make_map(&mb_lo, b->lo, p.cols, p.kdim, b->pitch, BLOCK_N)) != ATQ_OK) return r;
-  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI>;
+  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED>;
   static bool attr_done_dev[64] = {false};  // per instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -447,7 +544,7 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
   const int sms = sm_count(dev);
   const int grid = (int)(tiles < sms ? tiles : sms);
   *grid_used = grid;
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  kern<<<grid, gemm_threads(B_PACKED, BLOCK_N), Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("tgemm launch failed: %s", cudaGetErrorString(e));
@@ -531,6 +628,48 @@ int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf
   p.partials = dot_out ? (float*)ws : nullptr;
   int grid = 0;
   if ((r = dispatch<EPI_LINEAR>(a, b, p, stream, &grid)) != ATQ_OK) return r;
+  if (dot_out) {
+    reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, grid, dot_out);
+    ATQ_LAUNCH_CHECK();
+  }
+  return ATQ_OK;
+}
+
+int atq_tgemm_packed(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf16_operand* a,
+                     const uint8_t* b_packed, const float* scale, const float* bias, float* out, int64_t out_pitch,
+                     const float* dot_ref, int64_t dot_ref_pitch, float* dot_out, void* ws, size_t ws_bytes,
+                     atq_stream_t stream_) {
+  ATQ_CHECK_ARG(rows > 0 && cols > 0 && kdim > 0 && out != nullptr && out_pitch >= cols, "bad shape or null output");
+  ATQ_CHECK_ARG(b_packed != nullptr && (reinterpret_cast<uintptr_t>(b_packed) & 15u) == 0, "packed B must be 16-byte aligned");
+  ATQ_CHECK_ARG((kdim % 64) == 0, "packed-B GEMM needs kdim % 64 == 0 (16-byte codec rows per k-block)");
+  int r;
+  if ((r = check_operand(a, "a")) != ATQ_OK) return r;
+  ATQ_CHECK_ARG(a->pitch >= kdim, "operand pitch smaller than kdim");
+  ATQ_CHECK_ARG((dot_ref == nullptr) == (dot_out == nullptr), "dot_ref and dot_out go together");
+  if (dot_out != nullptr && (ws == nullptr || ws_bytes < atq_workspace_bytes_tgemm(rows, cols))) {
+    set_error("atq_tgemm_packed: workspace too small");
+    return ATQ_EWORKSPACE;
+  }
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.cols = cols; p.kdim = kdim;
+  p.out = out; p.out_pitch = out_pitch;
+  p.scale = scale; p.bias = bias;
+  p.dot_ref = dot_ref; p.dot_ref_pitch = dot_ref_pitch;
+  p.partials = dot_out ? (float*)ws : nullptr;
+  p.b_packed = b_packed; p.b_packed_pitch = kdim / 4;
+  int grid = 0;
+  const bool a2 = a->lo != nullptr;
+  if (cols <= 128) {
+    r = a2 ? launch_cfg<2, 1, 128, EPI_LINEAR, true>(a, nullptr, p, stream, &grid)
+           : launch_cfg<1, 1, 128, EPI_LINEAR, true>(a, nullptr, p, stream, &grid);
+  } else {
+    r = a2 ? launch_cfg<2, 1, 256, EPI_LINEAR, true>(a, nullptr, p, stream, &grid)
+           : launch_cfg<1, 1, 256, EPI_LINEAR, true>(a, nullptr, p, stream, &grid);
+  }
+  if (r != ATQ_OK) return r;
   if (dot_out) {
     reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, grid, dot_out);
     ATQ_LAUNCH_CHECK();

@@ -367,7 +367,7 @@ template <bool MIXED>
 __global__ void __launch_bounds__(256)
     build_operands_kernel(const float* __restrict__ w, const float* __restrict__ mask, int64_t M, int64_t K,
                           const float* __restrict__ thr_p, const float* __restrict__ alpha_p,
-                          uint8_t* __restrict__ packed,
+                          uint8_t* __restrict__ packed, uint8_t* __restrict__ packed_t,
                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pitch,
                           uint16_t* __restrict__ hi_t, uint16_t* __restrict__ lo_t, int64_t pitch_t,
                           TernStats* __restrict__ stats) {
@@ -426,6 +426,16 @@ __global__ void __launch_bounds__(256)
         uint32_t b = codes[rr][4 * bj] | (codes[rr][4 * bj + 1] << 2) | (codes[rr][4 * bj + 2] << 4) | (codes[rr][4 * bj + 3] << 6);
         // columns beyond K inside this byte cannot occur because K % 4 == 0
         packed[(m * K + k) >> 2] = (uint8_t)b;
+      }
+    }
+  }
+  if (packed_t != nullptr) {  // codec bytes of T^T [K, M/4] (M % 4 == 0 checked by the host)
+    for (int i = threadIdx.x; i < kTile * (kTile / 4); i += 256) {
+      int kk = i >> 4, bj = i & 15;
+      int64_t k = k0 + kk, m = m0 + 4 * bj;
+      if (k < K && m < M) {
+        uint32_t b = codes[4 * bj][kk] | (codes[4 * bj + 1][kk] << 2) | (codes[4 * bj + 2][kk] << 4) | (codes[4 * bj + 3][kk] << 6);
+        packed_t[(k * M + m) >> 2] = (uint8_t)b;
       }
     }
   }
@@ -670,17 +680,18 @@ int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int
 }
 
 int atq_build_ternary_operands(int device, const float* w, int64_t M, int64_t K, const float* thr, uint8_t* packed,
-                               uint16_t* tb, int64_t pitch, uint16_t* tb_t, int64_t pitch_t, void* stats,
-                               atq_stream_t stream_) {
+                               uint8_t* packed_t, uint16_t* tb, int64_t pitch, uint16_t* tb_t, int64_t pitch_t,
+                               void* stats, atq_stream_t stream_) {
   ATQ_CHECK_ARG(w && thr && M > 0 && K > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG(packed == nullptr || (K % 4) == 0, "packed output needs K % 4 == 0 (use atq_ternarize_pack2)");
+  ATQ_CHECK_ARG(packed_t == nullptr || (M % 4) == 0, "packed_t output needs M % 4 == 0");
   ATQ_CHECK_ARG(tb == nullptr || (pitch >= K && pitch % 8 == 0), "bad pitch");
   ATQ_CHECK_ARG(tb_t == nullptr || (pitch_t >= M && pitch_t % 8 == 0), "bad pitch_t");
   ATQ_ENSURE_DEVICE(device);
   dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((M + kTile - 1) / kTile));
   ATQ_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
-  build_operands_kernel<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, nullptr, M, K, thr, nullptr, packed, tb, nullptr, pitch,
-                                                                         tb_t, nullptr, pitch_t, (TernStats*)stats);
+  build_operands_kernel<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, nullptr, M, K, thr, nullptr, packed, packed_t, tb, nullptr,
+                                                                         pitch, tb_t, nullptr, pitch_t, (TernStats*)stats);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }
@@ -695,8 +706,8 @@ int atq_build_mixed_operands(int device, const float* w, const float* mask, int6
   ATQ_ENSURE_DEVICE(device);
   dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((M + kTile - 1) / kTile));
   ATQ_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
-  build_operands_kernel<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, mask, M, K, thr, alpha, packed, hi, lo, pitch, hi_t, lo_t,
-                                                                        pitch_t, nullptr);
+  build_operands_kernel<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, mask, M, K, thr, alpha, packed, nullptr, hi, lo, pitch, hi_t,
+                                                                        lo_t, pitch_t, nullptr);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }

@@ -202,15 +202,18 @@ def kernel_rooflines(device, peaks, flush, quick=True):
     tb = torch.empty((M, K), dtype=torch.bfloat16, device=device)
     tbt = torch.empty((K, M), dtype=torch.bfloat16, device=device)
     import atq._native as nv
+    packed = torch.empty(M * K // 4, dtype=torch.uint8, device=device)
     nv.call("atq_build_ternary_operands", 0 if device.index is None else device.index, w.data_ptr(), M, K, thr.data_ptr(),
-            None, tb.data_ptr(), K, tbt.data_ptr(), M, None, nv.stream_ptr(device.index or 0))
+            packed.data_ptr(), None, tb.data_ptr(), K, tbt.data_ptr(), M, None, nv.stream_ptr(device.index or 0))
     for mode, want_lo in (("parity(hi+lo)", True), ("fast(bf16)", False)):
         xa = eng.split_bf16(x, want_lo)
-        ms = _event_time(lambda: eng.tgemm(xa, (tb, None, K), N, M, K), 5, flush)
-        ach = 2.0 * N * M * K / (ms * 1e-3) / 1e12
-        out.append({"kernel": f"tgemm_kernel fwd {mode}", "workload": f"config3 TernaryLinear {M}x{K}, {N} tokens",
-                    "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
-                    "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None})
+        for bsrc, fn in (("B = 2-bit packed, unpacked in smem", lambda: eng.tgemm_packed(xa, packed, N, M, K)),
+                         ("B = bf16 via TMA", lambda: eng.tgemm(xa, (tb, None, K), N, M, K))):
+            ms = _event_time(fn, 5, flush)
+            ach = 2.0 * N * M * K / (ms * 1e-3) / 1e12
+            out.append({"kernel": f"tgemm_kernel fwd {mode}, {bsrc}", "workload": f"config3 TernaryLinear {M}x{K}, {N} tokens",
+                        "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
+                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None})
     # ---- config 5: quantize + pack, one 4096x4096 layer (64 MiB fp32; L2 flushed between runs)
     n = M * K
     ms = _event_time(lambda: eng.adaptive_threshold(w, 0.3), 5, flush)

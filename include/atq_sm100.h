@@ -116,13 +116,14 @@ int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int
                      uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, float* colsum, atq_stream_t stream);
 
 /* Quantize a layer into everything its GEMMs consume, in one pass over W [M,K]:
- *  packed   : 2-bit codec bytes of T (public format, flat row-major), nullable
+ *  packed   : 2-bit codec bytes of T (public format, flat row-major), nullable; K % 4 == 0
+ *  packed_t : 2-bit codec bytes of T^T ([K, M/4]; dX operand of atq_tgemm_packed), nullable; M % 4 == 0
  *  tb       : T as bf16 [M, pitch]  (forward B operand), nullable
  *  tb_t     : T^T as bf16 [K, pitch_t] (dX B operand), nullable
  * replaces atq/quantizers.py:41-43 + the `w_ternary * alpha` materialisation of atq/layers.py:43. */
 int atq_build_ternary_operands(int device, const float* w, int64_t M, int64_t K, const float* thr,
-                               uint8_t* packed, uint16_t* tb, int64_t pitch, uint16_t* tb_t, int64_t pitch_t,
-                               void* stats, atq_stream_t stream);
+                               uint8_t* packed, uint8_t* packed_t, uint16_t* tb, int64_t pitch,
+                               uint16_t* tb_t, int64_t pitch_t, void* stats, atq_stream_t stream);
 /* Residual-precision-boost mixed weight (atq/precision_boost.py:72):
  *  Wm = T*alpha*(1-mask) + W*mask, emitted as bf16 hi/lo pairs [M,pitch] and transposed
  *  [K,pitch_t]; lo pointers nullable (fast mode).  packed as above (nullable). */
@@ -155,6 +156,16 @@ int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim,
               float* out, int64_t out_pitch,
               const float* dot_ref, int64_t dot_ref_pitch, float* dot_out,
               void* ws, size_t ws_bytes, atq_stream_t stream);
+/* Same contraction with B given as the 2-bit codec bytes of T ([cols, kdim/4] row-major, i.e. the
+ * public packed format of a [cols, kdim] ternary matrix; kdim % 64 == 0, 16-byte aligned).
+ * Converter warps expand each 16-byte codec row segment to a 128-byte bf16 row of the
+ * SWIZZLE_128B B tile in shared memory; HBM/L2 only ever see 2 bits per weight.
+ * This is the native form of atq/bit_packing.py:149-176 (fast_ternary_matmul). */
+int atq_tgemm_packed(int device, int64_t rows, int64_t cols, int64_t kdim,
+                     const atq_bf16_operand* a, const uint8_t* b_packed,
+                     const float* scale, const float* bias, float* out, int64_t out_pitch,
+                     const float* dot_ref, int64_t dot_ref_pitch, float* dot_out,
+                     void* ws, size_t ws_bytes, atq_stream_t stream);
 /* named wrappers (same arguments), kept for readability at the call sites */
 int atq_tgemm_fwd(int device, int64_t n_tokens, int64_t out_features, int64_t in_features,
                   const atq_bf16_operand* x, const atq_bf16_operand* w,

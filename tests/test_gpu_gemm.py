@@ -232,3 +232,31 @@ def test_prepare_quantization_batched_equals_lazy():
         mod[2].weight.copy_(ref[2].weight)
         assert atq.prepare_quantization(mod) == 2
         assert torch.allclose(mod(x.to(DEV)).cpu(), ref(x), **TOL)
+
+
+@pytest.mark.parametrize("rows,cols,k", [(128, 128, 64), (300, 200, 128), (16, 1, 64), (800, 192, 192), (257, 10, 128),
+                                         (1000, 384, 3136), (1024, 4096, 4096), (130, 520, 704)])
+def test_tgemm_packed_b_unpacked_in_smem(rows, cols, k):
+    """K7 with B given as 2-bit codec bytes: bit-for-bit the same accumulation as the bf16-B path
+    (T is exact in bf16), and within tolerance of the fp64 answer."""
+    g = torch.Generator().manual_seed(rows + cols + k)
+    a = torch.randn(rows, k, generator=g)
+    t = torch.randint(-1, 2, (cols, k), generator=g).float()
+    packed, flag = eng.pack2_from_f32(t.to(DEV).reshape(-1))
+    assert int(flag) == 0 and eng.packed_gemm_ok(k, packed)
+    scale = torch.tensor([0.9], device=DEV)
+    bias = torch.randn(cols, generator=g).to(DEV)
+    ref_x = torch.randn(rows, cols, generator=g).to(DEV)
+    tb = eng.split_bf16(t.to(DEV), False)
+    for want_lo in (True, False):
+        a_op = eng.split_bf16(a.to(DEV), want_lo)
+        y_p, d_p = eng.tgemm_packed(a_op, packed, rows, cols, k, scale=scale, bias=bias, dot_ref=ref_x)
+        y_b, d_b = eng.tgemm(a_op, tb, rows, cols, k, scale=scale, bias=bias, dot_ref=ref_x)
+        assert torch.equal(y_p, y_b)
+        assert torch.allclose(d_p, d_b, rtol=1e-5, atol=1e-4)
+    want = _gemm_ref(a, t) * 0.9 + bias.cpu().double()
+    a_bf = a.bfloat16().float()  # last loop iteration: single bf16 term -> exact products of the rounded A
+    assert torch.allclose(y_p.cpu().double(), _gemm_ref(a_bf, t) * 0.9 + bias.cpu().double(), rtol=1e-4, atol=1e-3)
+    a2 = eng.split_bf16(a.to(DEV), True)
+    y, _ = eng.tgemm_packed(a2, packed, rows, cols, k, scale=scale, bias=bias)
+    assert torch.allclose(y.cpu().double(), want, **TOL)
