@@ -24,6 +24,12 @@ from . import _native as nv
 
 _MODE = os.environ.get("ATQ_GEMM_MODE", "parity")
 _STE = os.environ.get("ATQ_STE", "0") == "1"
+# B operand of the TernaryLinear GEMMs: "always" = 2-bit codec bytes expanded in shared memory,
+# "never" = bf16 copy through TMA, "auto" = packed while the GEMM is weight-bandwidth bound
+# (few tokens) and bf16-TMA once it is tensor-bound (the 1-CTA packed kernel is shared-memory
+# bandwidth limited at ~60 % of the bf16 peak, the TMA kernel reaches ~90 %).
+_PACKED = os.environ.get("ATQ_PACKED_GEMM", "auto")
+_PACKED_AUTO_MAX_TOKENS = 256
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -44,6 +50,17 @@ def set_ste(enabled: bool) -> None:
 
 def _use_lo() -> bool:
     return _MODE == "parity"
+
+
+def set_packed_gemm(policy: str) -> None:
+    global _PACKED
+    if policy not in ("auto", "always", "never"):
+        raise ValueError("policy must be 'auto', 'always' or 'never'")
+    _PACKED = policy
+
+
+def _want_packed(tokens: int) -> bool:
+    return _PACKED == "always" or (_PACKED == "auto" and tokens <= _PACKED_AUTO_MAX_TOKENS)
 
 
 # ---------------------------------------------------------------------------------------
@@ -295,10 +312,9 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
     if mask is None:
         # TernaryLinear: the GEMMs read the 2-bit codec bytes directly whenever the contraction
         # dimension allows 16-byte codec rows per k-block; bf16 copies only for odd shapes
-        fwd_packed, dx_packed = (K % 64 == 0), (M % 64 == 0)
-        hi = None if fwd_packed else torch.empty((M, pitch), dtype=bf, device=w.device)
-        hi_t = None if dx_packed else torch.empty((K, pitch_t), dtype=bf, device=w.device)
-        if dx_packed:
+        hi = torch.empty((M, pitch), dtype=bf, device=w.device)
+        hi_t = torch.empty((K, pitch_t), dtype=bf, device=w.device)
+        if M % 64 == 0:
             packed_t = torch.empty(n // 4, dtype=torch.uint8, device=w.device)
         lo = lo_t = None
         nv.call("atq_build_ternary_operands", dev, w.data_ptr(), M, K, thr.data_ptr(),
@@ -366,7 +382,8 @@ class _TernaryLinearFn(torch.autograd.Function):
         else:
             xa = split_bf16(x2, _use_lo())
             b_ = None if bias is None else bias.detach()
-            if ops.w is None:   # packed 2-bit weights, unpacked to bf16 tiles inside the GEMM
+            if _want_packed(N) and packed_gemm_ok(K, ops.packed):
+                # packed 2-bit weights, expanded to bf16 tiles inside the GEMM
                 y, _ = tgemm_packed(xa, ops.packed, N, M, K, scale=al, bias=b_)
             else:
                 y, _ = tgemm(xa, ops.w, N, M, K, scale=al, bias=b_)
@@ -390,7 +407,7 @@ class _TernaryLinearFn(torch.autograd.Function):
             return (gy.new_zeros(ctx.xshape), None, al.new_zeros(1), g2.new_zeros(M) if ctx.has_bias else None, None)
         ga = split_bf16(g2, _use_lo())
         # dX = alpha * (dY . T);  d(alpha) = sum((dY . T) .* X) fused in the same epilogue
-        if ctx.ops_w_t is None:
+        if _want_packed(N) and packed_gemm_ok(M, ctx.packed_t):
             dx, dalpha = tgemm_packed(ga, ctx.packed_t, N, K, M, scale=al, dot_ref=x2)
         else:
             dx, dalpha = tgemm(ga, ctx.ops_w_t, N, K, M, scale=al, dot_ref=x2)

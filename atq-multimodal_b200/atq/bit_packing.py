@@ -65,7 +65,7 @@ class TernaryBitPacking:
             return x.new_zeros(*x.shape[:-1], M) * alpha
         xa = eng.split_bf16(x2, eng.get_gemm_mode() == "parity")
         packed = packed.contiguous()
-        if eng.packed_gemm_ok(K, packed):
+        if eng.packed_gemm_ok(K, packed) and eng._PACKED != "never":
             # the GEMM reads the codec bytes and expands them in shared memory
             y, _ = eng.tgemm_packed(xa, packed, x2.shape[0], M, K)
         else:

@@ -50,10 +50,11 @@ def gather_embeddings(local: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class FlatGradAllReduce:
-    """Single flat fp32 buffer aliasing every parameter gradient that the step produces, reduced with
-    one NCCL all-reduce per bucket.  Parameters that never receive a gradient (TernaryLinear.weight,
-    modules off the training path) keep grad=None so the optimizer skips them exactly as
-    in the single-process reference."""
+    """One flat fp32 buffer for every parameter gradient that the step produces, reduced with one NCCL
+    all-reduce per bucket.  After backward the fresh gradients are packed into the buffer with a single
+    multi-tensor copy, reduced, and `p.grad` is re-pointed at views of the buffer (no copy back).
+    Parameters that never receive a gradient (TernaryLinear.weight, modules off the training path,
+    SURVEY H8) keep grad=None so the optimizer skips them exactly as in the single-process reference."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 256 << 20, group=None):
         self.params = [p for p in params if p.requires_grad]
@@ -61,11 +62,12 @@ class FlatGradAllReduce:
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.flat: Optional[torch.Tensor] = None
         self.active: List[torch.nn.Parameter] = []
+        self.views: List[torch.Tensor] = []
 
     def _bind(self):
         self.active = [p for p in self.params if p.grad is not None]
         total = sum(p.numel() for p in self.active)
-        self.flat = torch.zeros(total, dtype=torch.float32, device=self.active[0].device)
+        self.flat = torch.empty(total, dtype=torch.float32, device=self.active[0].device)
         self.views = []
         off = 0
         for p in self.active:
@@ -73,25 +75,24 @@ class FlatGradAllReduce:
             off += p.numel()
 
     def zero_grad(self):
-        """Use instead of optimizer.zero_grad(set_to_none=True) once bound, to keep the aliasing."""
-        if self.flat is None:
-            for p in self.params:
-                p.grad = None
-        else:
-            self.flat.zero_()
+        """Drop every gradient so autograd writes fresh tensors (no read-modify-write accumulation)."""
+        for p in self.params:
+            p.grad = None
 
     def reduce(self):
         if self.flat is None:
             self._bind()  # first step: discover which parameters this graph produces gradients for
+        grads = []
         for p, view in zip(self.active, self.views):
-            if p.grad is None:
+            if p.grad is None:  # parameter unused this step: contributes zeros
                 view.zero_()
-                p.grad = view
-            elif p.grad.data_ptr() != view.data_ptr():  # autograd created a fresh tensor: adopt it
-                view.copy_(p.grad)
-                p.grad = view
-        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
-            return
-        n = self.flat.numel()
-        for start in range(0, n, self.bucket_elems):
-            dist.all_reduce(self.flat[start: min(n, start + self.bucket_elems)], op=dist.ReduceOp.SUM, group=self.group)
+                grads.append(view)
+            else:
+                grads.append(p.grad)
+        torch._foreach_copy_(self.views, grads)  # multi-tensor pack into the flat buffer
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            n = self.flat.numel()
+            for start in range(0, n, self.bucket_elems):
+                dist.all_reduce(self.flat[start: min(n, start + self.bucket_elems)], op=dist.ReduceOp.SUM, group=self.group)
+        for p, view in zip(self.active, self.views):
+            p.grad = view

@@ -473,15 +473,17 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------
 // column sums (bias gradient): deterministic two-stage reduction
 // ------------------------------------------------------------------------------------
-constexpr int kColsumRowsPerCta = 256;
+// rows per CTA: 64 for short inputs (enough CTAs to hide latency), up to 512 for long ones
+static inline int colsum_rows_per_cta(int64_t rows) { return rows <= 8192 ? 64 : (rows <= 65536 ? 256 : 512); }
 __global__ void __launch_bounds__(256)
-    colsum_stage1_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ part) {
-  // CTA = 32 columns x kColsumRowsPerCta rows; 8 warps take interleaved rows
+    colsum_stage1_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, float* __restrict__ part,
+                         int rows_per_cta) {
+  // CTA = 32 columns x rows_per_cta rows; 8 warps take interleaved rows
   __shared__ float s[8][33];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + lane;
-  const int64_t r0 = (int64_t)blockIdx.y * kColsumRowsPerCta;
-  const int64_t r1 = min(rows, r0 + kColsumRowsPerCta);
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r1 = min(rows, r0 + rows_per_cta);
   float acc = 0.f;
   if (c < cols)
     for (int64_t r = r0 + wid; r < r1; r += 8) acc += __ldg(x + r * ld + c);
@@ -713,7 +715,8 @@ int atq_build_mixed_operands(int device, const float* w, const float* mask, int6
 }
 
 size_t atq_workspace_bytes_colsum(int64_t rows, int64_t cols) {
-  int64_t parts = (rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta;
+  const int rpc = colsum_rows_per_cta(rows);
+  int64_t parts = (rows + rpc - 1) / rpc;
   return (size_t)(parts * cols * sizeof(float));
 }
 
@@ -726,15 +729,16 @@ int atq_colsum_f32(int device, const float* x, int64_t rows, int64_t cols, int64
     return ATQ_EWORKSPACE;
   }
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (rows <= 4096) {
+  if (rows <= 64) {  // a single row block: one launch
     colsum_small_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>(x, rows, cols, ld, out);
     ATQ_LAUNCH_CHECK();
     return ATQ_OK;
   }
-  int64_t parts = (rows + kColsumRowsPerCta - 1) / kColsumRowsPerCta;
+  const int rpc = colsum_rows_per_cta(rows);
+  int64_t parts = (rows + rpc - 1) / rpc;
   dim3 g1((unsigned)((cols + 31) / 32), (unsigned)parts);
   ATQ_CHECK_ARG(parts <= 65535, "rows too large for one launch");
-  colsum_stage1_kernel<<<g1, 256, 0, stream>>>(x, rows, cols, ld, (float*)ws);
+  colsum_stage1_kernel<<<g1, 256, 0, stream>>>(x, rows, cols, ld, (float*)ws, rpc);
   ATQ_LAUNCH_CHECK();
   colsum_stage2_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>((const float*)ws, parts, cols, out);
   ATQ_LAUNCH_CHECK();

@@ -34,7 +34,7 @@ def test_workspace_queries_are_host_only():
     import atq._native as nv
     assert nv.lib.atq_workspace_bytes_select_kth_abs(1 << 20) >= 16 * 1024
     assert nv.lib.atq_workspace_bytes_tgemm(4096, 4096) >= 4 * 32 * 64
-    assert nv.lib.atq_workspace_bytes_colsum(1000, 768) == 4 * 768 * 4
+    assert nv.lib.atq_workspace_bytes_colsum(1000, 768) == 16 * 768 * 4
 
 
 def test_public_surface_matches_reference():

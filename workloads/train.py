@@ -58,9 +58,12 @@ def build_retrieval(layers, cfg: RetrievalCfg, seed=42):
     return model, criterion, manager
 
 
-def make_optimizer(model, cfg: RetrievalCfg, capturable=False):
+def make_optimizer(model, cfg: RetrievalCfg, capturable=False, fused=False):
+    # train_multimodal.py:361-366 (AdamW, betas (0.9, 0.98)); `fused` only selects torch's single-kernel
+    # CUDA implementation of the same update
+    kw = dict(fused=True) if fused else {}
     return torch.optim.AdamW(model.parameters(), lr=cfg.lr, weight_decay=1e-4, betas=(0.9, 0.98),
-                             capturable=capturable)
+                             capturable=capturable, **kw)
 
 
 def synthetic_batches(cfg: RetrievalCfg, count, seed, pin=False):
