@@ -71,7 +71,11 @@ class FlatGradAllReduce:
         self.views = []
         off = 0
         for p in self.active:
-            self.views.append(self.flat[off: off + p.numel()].view_as(p))
+            # same sizes AND strides as the parameter (channels-last conv weights stay channels-last:
+            # fused optimizers require param/grad layouts to match); dense tensors only
+            piece = self.flat[off: off + p.numel()]
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            self.views.append(piece.as_strided(p.size(), p.stride()) if dense else piece.view_as(p))
             off += p.numel()
 
     def zero_grad(self):

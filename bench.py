@@ -191,6 +191,15 @@ def _event_time(fn, iters, flush=None):
     return total / iters  # ms
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures
+# (profiles/r01_ncu_full_tgemm_v2.csv, profiles/r01_ncu_full_streaming_v2.csv); same shapes as below
+NCU_TRAFFIC = {
+    "tgemm parity tma": 255.7e6 + 109.8e6,
+    "tgemm parity packed": 138.8e6 + 92.0e6,
+    "select 4096": 3 * 67.1e6 + 1.5e6,
+}
+
+
 def kernel_rooflines(device, peaks, flush, quick=True):
     """BASELINE config 3 (GEMM, tensor-bound) and config 5 (quantize/pack, HBM-bound) shapes."""
     import atq._engine as eng
@@ -216,16 +225,18 @@ def kernel_rooflines(device, peaks, flush, quick=True):
                          ("B = bf16 via TMA", lambda: eng.tgemm(xa, (tb, None, K), N, M, K))):
             ms = _event_time(fn, 5, flush)
             ach = 2.0 * N * M * K / (ms * 1e-3) / 1e12
+            traffic = NCU_TRAFFIC.get("tgemm parity " + ("packed" if "packed" in bsrc else "tma")) if want_lo else None
             out.append({"kernel": f"tgemm_kernel fwd {mode}, {bsrc}", "workload": f"config3 TernaryLinear {M}x{K}, {N} tokens",
                         "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
-                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None})
+                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": traffic,
+                        "algorithmic_bytes": 2 * N * K * (2 if want_lo else 1) + (M * K // 4 if "packed" in bsrc else 2 * M * K) + 4 * N * M})
     # ---- config 5: quantize + pack, one 4096x4096 layer (64 MiB fp32; L2 flushed between runs)
     n = M * K
     ms = _event_time(lambda: eng.adaptive_threshold(w, 0.3), 5, flush)
     out.append({"kernel": "select_pass_kernel x3 (exact k-th |W|)", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
                 "achieved": round(4.0 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
                 "frac": round(4.0 * n / (ms * 1e-3) / 1e9 / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4),
-                "traffic": None, "note": "4 B/elem over the whole 3-pass select"})
+                "traffic": NCU_TRAFFIC["select 4096"], "note": "4 B/elem over the whole 3-pass select (3 full reads: traffic = 3x algorithmic)"})
     ms = _event_time(lambda: eng.ternarize_pack2(w, thr), 5, flush)
     out.append({"kernel": "ternarize_kernel -> 2-bit", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
                 "achieved": round(4.25 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
@@ -336,6 +347,8 @@ def run_ours(args, cfg):
     def eager_step(batch):
         return T.retrieval_step(model, manager, opt, batch, gather, sync, atq.prepare_quantization)
 
+    sampler = ClockSampler(local)
+    sampler.start()  # samples from warm-up to the end of the e2e leg: the GPU is under load throughout
     run_step = eager_step
     for i in range(args.warmup):
         eager_step(resident[i % pool])
@@ -359,8 +372,6 @@ def run_ours(args, cfg):
             loss = eager_step(to_device(host[i % pool], device))
         losses.append(float(loss.detach()))       # device -> host read of the step's loss
 
-    sampler = ClockSampler(local)
-    sampler.start()
     k0 = nv.kernel_launch_count()
     ms_total = timed_steps(step_resident, args.steps, flush, world)
     launches = nv.kernel_launch_count() - k0

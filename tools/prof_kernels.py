@@ -17,25 +17,30 @@ g = torch.Generator(device=dev).manual_seed(0)
 w = (torch.rand(M, K, device=dev, generator=g) * 2 - 1) / K ** 0.5
 x = torch.randn(N, K, device=dev, generator=g)
 gy = torch.randn(N, M, device=dev, generator=g)
-reps = 3
+reps = 2
 if which in ("all", "stream"):
+    wbig = (torch.rand(8192, 8192, device=dev, generator=g) * 2 - 1) / 8192 ** 0.5
     for _ in range(reps):
-        thr = eng.adaptive_threshold(w, 0.3)
-        packed = eng.ternarize_pack2(w, thr)
-        t = eng.ternarize_f32(w, thr)
-        u = eng.unpack2(packed, M * K)
+        thr = eng.adaptive_threshold(w, 0.3)          # plain 3-pass radix select (16M)
+        thr_big = eng.adaptive_threshold(wbig, 0.3)   # sampled select (67M)
+        packed = eng.ternarize_pack2(wbig, thr_big)
+        t = eng.ternarize_f32(wbig, thr_big)
+        u = eng.unpack2(packed, wbig.numel())
         p2, flag = eng.pack2_from_f32(u)
         xa = eng.split_bf16(x, True)
         xt = eng.split_bf16_t(x, True)
+        del t, u, p2
 if which in ("all", "gemm"):
     tl = atq.TernaryLinear(K, M).to(dev)
     rpb = atq.ResidualPrecisionBoostLinear(K, M, 0.05, True, 0.3).to(dev)
     for mode in ("parity", "fast"):
         atq.set_gemm_mode(mode)
-        for mod in (tl, rpb):
-            for _ in range(reps):
-                xi = x.clone().requires_grad_(True)
-                y = mod(xi)
-                y.backward(gy)
+        for policy in ("never", "always"):
+            atq.set_packed_gemm(policy)
+            for mod in ((tl, rpb) if policy == "never" else (tl,)):
+                for _ in range(reps):
+                    xi = x.clone().requires_grad_(True)
+                    y = mod(xi)
+                    y.backward(gy)
 torch.cuda.synchronize()
 print("done")
