@@ -35,28 +35,37 @@ struct SelectState {
 // data, massive ties -- a device-side flag routes to the full three-pass select.  Exactness is
 // therefore unconditional; only the cost is data dependent.
 constexpr int kSampleN = 8192;
-constexpr long long kSampleMinN = 1ll << 25;  // measured crossover: 74 us (plain) vs 85 us (sampled) at 16M, 2x faster at 67M
-constexpr int kChunk = 8192;      // elements per filter CTA
+// sampling pays off for one layer from ~32M elements (fixed cost: 10 small launches) and from ~4M
+// elements when the call batches >= 64M elements in total (launches shared by all layers)
+constexpr long long kSampleMinN = 1ll << 25;
+constexpr long long kSampleMinNBatched = 1ll << 22;
+constexpr long long kBatchedTotal = 1ll << 26;
 constexpr int kFilterThreads = 256;
-constexpr int kLocalCap = 2048;   // shared-memory candidate slots per filter CTA
+constexpr int kWarpChunk = 512;   // elements per warp step of the filter pass (4 float4 per lane)
 
 struct SampleState {
   unsigned int lo, hi;             // candidate bracket on |x| bit patterns, inclusive
-  unsigned int n_cand;             // candidates appended
+  unsigned int n_cand;             // candidate-buffer slots reserved (slabs; unused slots hold a sentinel)
   unsigned int fallback;           // 1 => the bracket missed; the full radix select decides
+  unsigned int n_valid;            // real candidates among the reserved slots
+  unsigned int pad0;
   unsigned long long count_below;  // #{u < lo}
   unsigned long long cap;          // capacity of the candidate buffer
 };
 
 enum { MODE_PLAIN = 0, MODE_CAND = 1, MODE_FALLBACK = 2 };
 
+struct PivotTable;
 struct SelectBatch {
   const float* x[kMaxBatch];
   long long n[kMaxBatch];
   long long k[kMaxBatch];
   float* thr_out[kMaxBatch];
-  SelectState* states;  // [count]
-  SampleState* ss;      // MODE_CAND / MODE_FALLBACK only (single layer)
+  uint32_t* cand[kMaxBatch];  // sampled layers: candidate key buffers
+  SelectState* states;        // [count]  plain passes / full (fallback) passes
+  SelectState* cand_states;   // [count]  candidate passes
+  SampleState* ss;            // [count]
+  PivotTable* pt;             // [count]
 };
 
 __global__ void __launch_bounds__(kSelThreads) select_init_kernel(SelectBatch b) {
@@ -91,24 +100,25 @@ __global__ void __launch_bounds__(kSelThreads) select_pass_kernel(SelectBatch b)
   __shared__ int s_last;
 
   const int layer = blockIdx.y;
-  const float* __restrict__ x = b.x[layer];
+  const float* __restrict__ x = (MODE == MODE_CAND) ? reinterpret_cast<const float*>(b.cand[layer]) : b.x[layer];
   long long n = b.n[layer];
-  SelectState* st = b.states + layer;
+  SelectState* st = (MODE == MODE_CAND ? b.cand_states : b.states) + layer;
+  SampleState* ss = (MODE == MODE_PLAIN) ? nullptr : b.ss + layer;
   uint32_t bias = 0u;
   if constexpr (MODE == MODE_CAND) {
-    if (b.ss->fallback) return;  // bracket already known to have missed
-    const unsigned long long nc = b.ss->n_cand;
-    n = (long long)(nc < b.ss->cap ? nc : b.ss->cap);
-    bias = b.ss->lo;  // keys are taken relative to the bracket's lower end
+    if (ss->fallback) return;  // bracket already known to have missed
+    const unsigned long long nc = ss->n_cand;
+    n = (long long)(nc < ss->cap ? nc : ss->cap);
+    bias = ss->lo;  // keys are taken relative to the bracket's lower end
   }
   if constexpr (MODE == MODE_FALLBACK) {
-    if (!b.ss->fallback) return;
+    if (!ss->fallback) return;
   }
   const uint32_t prefix = (PASS == 0) ? 0u : st->prefix;  // written by the previous launch
   bool skip_scan = false;
   if constexpr (MODE == MODE_CAND && PASS == 0) {
     // keys are |x| - lo: if the bracket spans fewer than 2^20 values every key's top digit is 0
-    skip_scan = (b.ss->hi - b.ss->lo) < (1u << 20);
+    skip_scan = (ss->hi - ss->lo) < (1u << 20);
   }
 
   for (int i = threadIdx.x; i < NB; i += kSelThreads) sh[i] = 0u;
@@ -185,11 +195,11 @@ __global__ void __launch_bounds__(kSelThreads) select_pass_kernel(SelectBatch b)
   unsigned long long k = __ldcg(&st->k_rem);
   if constexpr (MODE == MODE_CAND && PASS == 0) {
     // rank inside the candidate list; outside => the bracket missed, hand over to the full select
-    const long long kc = b.k[layer] - (long long)__ldcg(&b.ss->count_below);
-    const bool overflow = __ldcg(&b.ss->n_cand) > b.ss->cap;
-    if (kc < 0 || kc >= n || overflow) {
+    const long long kc = b.k[layer] - (long long)__ldcg(&ss->count_below);
+    const bool overflow = __ldcg(&ss->n_cand) > ss->cap;
+    if (kc < 0 || kc >= (long long)__ldcg(&ss->n_valid) || overflow) {
       if (threadIdx.x == 0) {
-        b.ss->fallback = 1u;
+        ss->fallback = 1u;
         st->blocks_done = 0u;
       }
       return;
@@ -215,11 +225,7 @@ __global__ void __launch_bounds__(kSelThreads) select_pass_kernel(SelectBatch b)
   if (threadIdx.x == 0) st->blocks_done = 0u;
 }
 
-// ---- sampling front-end ----------------------------------------------------------------------
-// Bracket from a strided sample WITHOUT sorting it: every CTA holds the whole 8192-element sample
-// in shared memory and ranks 8 "pivot" elements (every 16th sample) by counting, one warp per
-// pivot (ties broken by index, so ranks are distinct).  The 512 (rank, key) pairs go to a small
-// table; the filter CTAs pick the tightest pivots around the target rank from it.
+// ---- sampling front-end (batched: blockIdx.y = layer) -------------------------------------------
 constexpr int kPivots = 512;
 constexpr int kPivotsPerCta = 8;
 struct PivotTable {
@@ -227,34 +233,43 @@ struct PivotTable {
   unsigned int key[kPivots];
   unsigned int sample[kSampleN];
 };
-// one strided load per thread (the sample positions are 32 KB or more apart: pure DRAM latency)
-__global__ void __launch_bounds__(256) sample_gather_kernel(const float* __restrict__ x, long long n, uint32_t* __restrict__ sample) {
+
+// one strided load per thread (the sample positions are 2 KB or more apart: pure DRAM latency)
+__global__ void __launch_bounds__(256) sample_gather_kernel(SelectBatch b) {
+  const int layer = blockIdx.y;
   const int i = blockIdx.x * 256 + threadIdx.x;
+  const long long n = b.n[layer];
   const long long stride = n / kSampleN;
-  sample[i] = __float_as_uint(__ldg(x + (long long)i * stride + (stride >> 1))) & 0x7fffffffu;
+  b.pt[layer].sample[i] = __float_as_uint(__ldg(b.x[layer] + (long long)i * stride + (stride >> 1))) & 0x7fffffffu;
 }
 
-__global__ void __launch_bounds__(256)
-    sample_pivots_kernel(const uint32_t* __restrict__ sample, long long n, long long k, SampleState* ss, SelectState* st_full,
-                         SelectState* st_cand, PivotTable* pt, unsigned long long cap) {
+// Every CTA holds the layer's whole 8192-element sample in shared memory and ranks 8 "pivot"
+// elements (every 16th sample) by counting, one warp per pivot (ties broken by index, so ranks are
+// distinct) -- no sort.  CTA 0 of each layer also arms the layer's state.
+__global__ void __launch_bounds__(256) sample_pivots_kernel(SelectBatch b) {
   __shared__ __align__(16) uint32_t keys[kSampleN];
+  const int layer = blockIdx.y;
+  PivotTable* pt = b.pt + layer;
   {
-    const uint4* src = reinterpret_cast<const uint4*>(sample);
+    const uint4* src = reinterpret_cast<const uint4*>(pt->sample);
     uint4* dst = reinterpret_cast<uint4*>(keys);
 #pragma unroll
     for (int j = 0; j < kSampleN / 4 / 256; ++j) dst[threadIdx.x + 256 * j] = __ldg(src + threadIdx.x + 256 * j);
   }
   if (blockIdx.x == 0) {
+    SelectState* st_full = b.states + layer;
+    SelectState* st_cand = b.cand_states + layer;
     for (int i = threadIdx.x; i < kBins0; i += 256) {
       st_full->hist[i] = 0ull;
       st_cand->hist[i] = 0ull;
     }
     if (threadIdx.x == 0) {
+      SampleState* ss = b.ss + layer;
       ss->n_cand = 0u;
+      ss->n_valid = 0u;
       ss->fallback = 0u;
       ss->count_below = 0ull;
-      ss->cap = cap;
-      st_full->k_rem = (unsigned long long)k;
+      st_full->k_rem = (unsigned long long)b.k[layer];
       st_full->prefix = 0u;
       st_full->blocks_done = 0u;
       st_cand->k_rem = 0ull;
@@ -264,8 +279,8 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int p = blockIdx.x * kPivotsPerCta + wid;        // pivot id
-  const int e = p * (kSampleN / kPivots) + (kSampleN / kPivots) / 2;  // its index in the sample
+  const int p = blockIdx.x * kPivotsPerCta + wid;                      // pivot id
+  const int e = p * (kSampleN / kPivots) + (kSampleN / kPivots) / 2;   // its index in the sample
   const uint32_t me = keys[e];
   int rank = 0;
 #pragma unroll 8
@@ -282,144 +297,145 @@ __global__ void __launch_bounds__(256)
 }
 
 // bracket ends from the pivot table: lo = key of the highest-ranked pivot with rank <= target-delta
-// (0 if none), hi = key of the lowest-ranked pivot with rank >= target+delta (max if none).
-// Called by a whole CTA of >= 256 threads; result broadcast through shared memory.
-__device__ __forceinline__ void bracket_from_pivots(const PivotTable* pt, long long n, long long k, uint32_t* s_lohi,
-                                                    uint32_t& lo, uint32_t& hi) {
-  const double q = (double)k / (double)n;
+// (0 if none), hi = key of the lowest-ranked pivot with rank >= target+delta (max if none)
+__global__ void __launch_bounds__(256) bracket_kernel(SelectBatch b) {
+  __shared__ uint32_t s_lohi[2];
+  const int layer = blockIdx.x;
+  const PivotTable* pt = b.pt + layer;
+  const double q = (double)b.k[layer] / (double)b.n[layer];
   const long long r = (long long)(q * kSampleN);
   const long long delta = (long long)ceil(5.5 * sqrt((double)kSampleN * q * (1.0 - q))) + 2;
   const long long lo_t = r - delta, hi_t = r + delta + 1;
   if (threadIdx.x == 0) {
-    s_lohi[0] = 0u;           // max over candidates for lo
-    s_lohi[1] = 0x7fffffffu;  // min over candidates for hi
+    s_lohi[0] = 0u;
+    s_lohi[1] = 0x7fffffffu;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kPivots; i += blockDim.x) {
+  for (int i = threadIdx.x; i < kPivots; i += 256) {
     const long long rk = (long long)pt->rank[i];
     const uint32_t key = pt->key[i];
     if (rk <= lo_t) atomicMax(&s_lohi[0], key);  // keys are monotone in rank
     if (rk >= hi_t) atomicMin(&s_lohi[1], key);
   }
   __syncthreads();
-  lo = s_lohi[0];
-  hi = s_lohi[1];
+  if (threadIdx.x == 0) {
+    b.ss[layer].lo = s_lohi[0];
+    b.ss[layer].hi = s_lohi[1];
+  }
 }
 
-// one streaming pass: count |x| below the bracket, compact |x| inside it (x 16-byte aligned).
-// Each warp owns a private shared-memory segment and keeps its fill count in a register
-// (ballot + popc), so the hot loop has no atomics at all; one global atomic per CTA publishes.
-constexpr int kWarpCap = kLocalCap / (kFilterThreads / 32);  // 256 slots per warp
-__global__ void __launch_bounds__(kFilterThreads, 4)
-    filter_kernel(const float* __restrict__ x, long long n, long long k, SampleState* ss, const PivotTable* pt,
-                  uint32_t* __restrict__ cand) {
-  __shared__ uint32_t buf[kLocalCap + kFilterThreads / 32];
-  __shared__ unsigned int s_wcnt[kFilterThreads / 32], s_woff[kFilterThreads / 32], s_gbase;
-  __shared__ unsigned long long s_below[kFilterThreads / 32];
-  __shared__ uint32_t s_lohi[2];
-  uint32_t lo, hi;
-  bracket_from_pivots(pt, n, k, s_lohi, lo, hi);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {  // the candidate passes read the bracket from here
-    ss->lo = lo;
-    ss->hi = hi;
-  }
-  const long long start = (long long)blockIdx.x * kChunk;
-  const long long end = (start + kChunk < n) ? start + kChunk : n;
-  const int nvec = (int)((end - start) >> 2);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  uint32_t* wbuf = buf + wid * kWarpCap;
-  // Two branch-free sweeps over the 32 values this thread holds in registers: count, warp-scan the
-  // counts (5 shuffles per thread instead of a ballot + popc per element), then scatter with
-  // unconditional stores (non-candidates go to a dump slot).
-  constexpr int kPerThread = kChunk / 4 / kFilterThreads;
-  const uint32_t span = hi - lo;  // lo <= u <= hi  <=>  (u - lo) <= span   (hi >= lo always)
-  const bool full = (nvec == kChunk / 4);  // CTA-uniform: every slot of the chunk is real
-  uint32_t u[4 * kPerThread];
-#pragma unroll
-  for (int j = 0; j < kPerThread; ++j) {
-    const int g = (threadIdx.x & ~31) + j * kFilterThreads + lane;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (full || g < nvec) v = ldg_stream4(x + start + 4ll * g);
-    u[4 * j + 0] = __float_as_uint(v.x) & 0x7fffffffu;
-    u[4 * j + 1] = __float_as_uint(v.y) & 0x7fffffffu;
-    u[4 * j + 2] = __float_as_uint(v.z) & 0x7fffffffu;
-    u[4 * j + 3] = __float_as_uint(v.w) & 0x7fffffffu;
-  }
-  if (!full) {  // park the out-of-range slots above every bracket and every `lo`
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-      const int g = (threadIdx.x & ~31) + j * kFilterThreads + lane;
-      if (g >= nvec) { u[4 * j] = u[4 * j + 1] = u[4 * j + 2] = u[4 * j + 3] = 0xffffffffu; }
+// ONE streaming pass per layer: count |x| below the bracket, compact |x| inside it.
+// Warp-granular and barrier-free: a warp takes 1024 elements (8 float4 per lane, all loads issued
+// before the first use), tallies, scans the per-lane counts with shuffles, reserves room in the
+// layer's candidate buffer with ONE global atomic and scatters its candidates with predicated
+// stores.  No shared memory, no __syncthreads, no ballots.
+__global__ void __launch_bounds__(kFilterThreads) filter_kernel(SelectBatch b) {
+  const int layer = blockIdx.y;
+  const float* __restrict__ x = b.x[layer];
+  const long long n = b.n[layer];
+  SampleState* ss = b.ss + layer;
+  uint32_t* __restrict__ cand = b.cand[layer];
+  const uint32_t lo = ss->lo, hi = ss->hi;
+  const uint32_t span = hi - lo;  // lo <= u <= hi  <=>  (u - lo) <= span
+  const unsigned cap32 = (unsigned)(ss->cap < 0xffffffffull ? ss->cap : 0xffffffffull);
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = (long long)gridDim.x * (kFilterThreads / 32);
+  const long long warp_id = (long long)blockIdx.x * (kFilterThreads / 32) + (threadIdx.x >> 5);
+  constexpr int kV = kWarpChunk / 128;  // float4 per lane per chunk
+  const long long nfull = n / kWarpChunk;  // whole chunks; the ragged remainder is handled after the loop
+  unsigned int below = 0u;
+
+  // Candidate space is reserved in warp-private slabs of kSlab slots (one returning atomic per slab,
+  // ~1 per 8K input elements): same-address returning atomics run at ~1/ns chip-wide, so one per
+  // 512-element chunk would cap the pass at ~2 TB/s.  Unused slab tails are filled with a sentinel
+  // key that sorts above every real candidate.
+  constexpr unsigned kSlab = 512;
+  static_assert(kSlab >= kWarpChunk, "a chunk's candidates must fit one slab");
+  unsigned slab_base = 0, slab_used = kSlab, valid_total = 0;  // warp-uniform
+  bool have_slab = false;
+  auto close_slab = [&]() {
+    if (have_slab) {
+      for (unsigned i = slab_used + lane; i < kSlab; i += 32)
+        if (slab_base + i < cap32) cand[slab_base + i] = 0xffffffffu;
     }
-  }
-  unsigned int below = 0u, mine = 0u;
+  };
+  auto process = [&](const uint32_t (&u)[4 * kV]) {
+    unsigned int mine = 0u;
 #pragma unroll
-  for (int i = 0; i < 4 * kPerThread; ++i) {
-    below += (u[i] < lo) ? 1u : 0u;
-    mine += (u[i] - lo <= span) ? 1u : 0u;
-  }
-  uint32_t tail_u = 0xffffffffu;
-  if (wid == 0) {  // ragged tail of the last chunk (at most 3 elements)
-    const long long i = start + 4ll * nvec + lane;
-    if ((lane < 4) && i < end) tail_u = __float_as_uint(__ldg(x + i)) & 0x7fffffffu;
-    below += (tail_u < lo) ? 1u : 0u;
-    mine += (tail_u - lo <= span) ? 1u : 0u;
-  }
-  unsigned incl = mine;
+    for (int i = 0; i < 4 * kV; ++i) {
+      below += (u[i] < lo) ? 1u : 0u;
+      mine += (u[i] - lo <= span) ? 1u : 0u;
+    }
+    unsigned incl = mine;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const unsigned wcount = __shfl_sync(0xffffffffu, incl, 31);
-  if (wcount) {  // warp-uniform
-    unsigned pos = incl - mine;
-    const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(wbuf);
-    auto scatter = [&](uint32_t val) {
-      // predicated shared store, no branch: p = in-bracket && slot available
-      const uint32_t c = (val - lo <= span) ? 1u : 0u;
-      const uint32_t ok = (pos < (unsigned)kWarpCap) ? c : 0u;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}"
-          ::"r"(wbase + 4u * pos), "r"(val), "r"(ok)
-          : "memory");
-      pos += c;
-    };
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const unsigned wcount = __shfl_sync(0xffffffffu, incl, 31);
+    if (wcount) {  // warp-uniform
+      if (slab_used + wcount > kSlab) {
+        close_slab();
+        unsigned gbase = 0;
+        if (lane == 0) gbase = atomicAdd(&ss->n_cand, kSlab);
+        slab_base = __shfl_sync(0xffffffffu, gbase, 0);
+        slab_used = 0;
+        have_slab = true;
+      }
+      unsigned pos = slab_base + slab_used + (incl - mine);
 #pragma unroll
-    for (int i = 0; i < 4 * kPerThread; ++i) scatter(u[i]);
-    if (wid == 0) scatter(tail_u);
+      for (int i = 0; i < 4 * kV; ++i) {
+        const bool c = (u[i] - lo <= span);
+        if (c && pos < cap32) cand[pos] = u[i];
+        pos += c ? 1u : 0u;
+      }
+      slab_used += wcount;
+      valid_total += wcount;
+    }
+  };
+
+  // software pipeline: the next chunk's loads are in flight while this chunk is tallied / scattered
+  float4 nxt[kV];
+  long long ch = warp_id;
+  if (ch < nfull) {
+#pragma unroll
+    for (int j = 0; j < kV; ++j) nxt[j] = ldg_stream4(x + ch * kWarpChunk + 4ll * (j * 32 + lane));
   }
-  unsigned long long below64 = warp_sum((unsigned long long)below);
+  while (ch < nfull) {
+    uint32_t u[4 * kV];
+#pragma unroll
+    for (int j = 0; j < kV; ++j) {
+      u[4 * j + 0] = __float_as_uint(nxt[j].x) & 0x7fffffffu;
+      u[4 * j + 1] = __float_as_uint(nxt[j].y) & 0x7fffffffu;
+      u[4 * j + 2] = __float_as_uint(nxt[j].z) & 0x7fffffffu;
+      u[4 * j + 3] = __float_as_uint(nxt[j].w) & 0x7fffffffu;
+    }
+    const long long nx = ch + warps_total;
+    if (nx < nfull) {
+#pragma unroll
+      for (int j = 0; j < kV; ++j) nxt[j] = ldg_stream4(x + nx * kWarpChunk + 4ll * (j * 32 + lane));
+    }
+    process(u);
+    ch = nx;
+  }
+  if (warp_id == 0 && nfull * kWarpChunk < n) {  // ragged tail (< kWarpChunk elements), one warp
+    uint32_t u[4 * kV];
+#pragma unroll
+    for (int j = 0; j < kV; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long i = nfull * kWarpChunk + 4ll * (j * 32 + lane) + e;
+        u[4 * j + e] = (i < n) ? (__float_as_uint(__ldg(x + i)) & 0x7fffffffu) : 0xffffffffu;  // parked above any bracket
+      }
+    }
+    process(u);
+  }
+  close_slab();
+  below = (unsigned int)warp_sum((unsigned long long)below);
   if (lane == 0) {
-    s_below[wid] = below64;
-    s_wcnt[wid] = wcount;
+    if (below) atomicAdd(&ss->count_below, (unsigned long long)below);
+    if (valid_total) atomicAdd(&ss->n_valid, valid_total);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long t = 0ull;
-    unsigned total = 0;
-    bool over = false;
-    for (int i = 0; i < kFilterThreads / 32; ++i) {
-      t += s_below[i];
-      s_woff[i] = total;
-      total += s_wcnt[i];
-      over |= s_wcnt[i] > (unsigned)kWarpCap;
-    }
-    if (t) atomicAdd(&ss->count_below, t);
-    if (over) {
-      atomicExch(&ss->fallback, 1u);
-      s_gbase = 0xffffffffu;
-    } else {
-      s_gbase = total ? atomicAdd(&ss->n_cand, total) : 0u;
-    }
-  }
-  __syncthreads();
-  const unsigned gbase = s_gbase;
-  if (gbase == 0xffffffffu) return;
-  const unsigned long long cap = ss->cap;
-  const unsigned my = s_wcnt[wid], off = gbase + s_woff[wid];
-  for (unsigned i = lane; i < my; i += 32)
-    if ((unsigned long long)off + i < cap) cand[off + i] = wbuf[i];
 }
 
 // out-of-range branches of the reference's threshold stage (atq/quantizers.py:33-38)
@@ -430,132 +446,221 @@ __global__ void threshold_from_stats_kernel(const AbsStatsView* as, long long n,
 }
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static inline int64_t sample_min_n(int count, const int64_t* ns) {
+  int64_t total = 0;
+  for (int i = 0; i < count; ++i) total += ns[i];
+  return total >= kBatchedTotal ? kSampleMinNBatched : kSampleMinN;
+}
+constexpr int kFilterMaxCtas = 592;  // per layer: bounds the slab-tail waste (296 * 8 warps * 512 slots)
+static inline unsigned long long cand_capacity(int64_t n) {
+  return (unsigned long long)(n / 8 + 65536) + (unsigned long long)kFilterMaxCtas * (kFilterThreads / 32) * 512ull;
+}
 
 }  // namespace atq
 
 using namespace atq;
 
-static int select_batched_impl(int device, int count, const float* const* xs, const int64_t* ns, const int64_t* ks,
-                               float* const* thr_outs, void* ws, cudaStream_t stream) {
-  // all entries here satisfy 0 <= k < n
-  SelectState* states = reinterpret_cast<SelectState*>(ws);
-  for (int base = 0; base < count; base += kMaxBatch) {
-    const int cnt = (count - base < kMaxBatch) ? (count - base) : kMaxBatch;
-    SelectBatch b;
-    memset(&b, 0, sizeof(b));
-    int64_t max_n = 0;
-    for (int i = 0; i < cnt; ++i) {
-      b.x[i] = xs[base + i];
-      b.n[i] = ns[base + i];
-      b.k[i] = ks[base + i];
-      b.thr_out[i] = thr_outs[base + i];
-      if (ns[base + i] > max_n) max_n = ns[base + i];
-    }
-    b.states = states + base;
-    // CTAs per layer: 16 elements per thread per trip, capped so that the whole launch is
-    // about 8 CTAs per SM
-    int64_t need = (max_n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
-    int64_t cap = ((int64_t)sm_count(device) * 8 + cnt - 1) / cnt;
-    if (cap < 1) cap = 1;
-    int gx = (int)(need < cap ? need : cap);
-    if (gx < 1) gx = 1;
-    dim3 grid((unsigned)gx, (unsigned)cnt);
-    select_init_kernel<<<cnt, kSelThreads, 0, stream>>>(b);
-    select_pass_kernel<0, MODE_PLAIN><<<grid, kSelThreads, 0, stream>>>(b);
-    select_pass_kernel<1, MODE_PLAIN><<<grid, kSelThreads, 0, stream>>>(b);
-    select_pass_kernel<2, MODE_PLAIN><<<grid, kSelThreads, 0, stream>>>(b);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-      set_error("select: kernel launch failed: %s", cudaGetErrorString(e));
-      return ATQ_ECUDA;
-    }
-    note_launch(4);
-  }
-  return ATQ_OK;
-}
-
-static inline bool use_sampling(const float* x, int64_t n) {
-  return n >= kSampleMinN && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
-}
-static inline unsigned long long cand_capacity(int64_t n) { return (unsigned long long)(n / 8 + 65536); }
-static inline size_t big_layer_ws(int64_t n) {
-  return 2 * align256(sizeof(SelectState)) + align256(sizeof(SampleState)) + align256(sizeof(PivotTable)) +
-         align256((size_t)cand_capacity(n) * 4);
-}
-
-// large layer: sample -> filter -> select among candidates (-> full select only if the bracket missed)
-static int select_sampled_impl(int device, const float* x, int64_t n, int64_t k, float* thr_out, void* ws,
-                               cudaStream_t stream) {
-  char* base = reinterpret_cast<char*>(ws);
-  SelectState* st_full = reinterpret_cast<SelectState*>(base);
-  SelectState* st_cand = reinterpret_cast<SelectState*>(base + align256(sizeof(SelectState)));
-  SampleState* ss = reinterpret_cast<SampleState*>(base + 2 * align256(sizeof(SelectState)));
-  PivotTable* pt = reinterpret_cast<PivotTable*>(base + 2 * align256(sizeof(SelectState)) + align256(sizeof(SampleState)));
-  uint32_t* cand = reinterpret_cast<uint32_t*>(base + 2 * align256(sizeof(SelectState)) + align256(sizeof(SampleState)) +
-                                               align256(sizeof(PivotTable)));
-  const unsigned long long cap = cand_capacity(n);
-  sample_gather_kernel<<<kSampleN / 256, 256, 0, stream>>>(x, (long long)n, pt->sample);
-  sample_pivots_kernel<<<kPivots / kPivotsPerCta, 256, 0, stream>>>(pt->sample, (long long)n, (long long)k, ss, st_full, st_cand, pt, cap);
-  const int64_t chunks = (n + kChunk - 1) / kChunk;
-  filter_kernel<<<(unsigned)chunks, kFilterThreads, 0, stream>>>(x, (long long)n, (long long)k, ss, pt, cand);
-  SelectBatch b;
-  memset(&b, 0, sizeof(b));
-  b.x[0] = reinterpret_cast<const float*>(cand);
-  b.n[0] = (long long)cap;
-  b.k[0] = k;
-  b.thr_out[0] = thr_out;
-  b.states = st_cand;
-  b.ss = ss;
-  int64_t need = ((int64_t)cap + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
-  int64_t capg = (int64_t)sm_count(device) * 4;
-  int gx = (int)(need < capg ? need : capg);
-  select_pass_kernel<0, MODE_CAND><<<dim3(gx, 1), kSelThreads, 0, stream>>>(b);
-  select_pass_kernel<1, MODE_CAND><<<dim3(gx, 1), kSelThreads, 0, stream>>>(b);
-  select_pass_kernel<2, MODE_CAND><<<dim3(gx, 1), kSelThreads, 0, stream>>>(b);
-  SelectBatch f;
-  memset(&f, 0, sizeof(f));
-  f.x[0] = x;
-  f.n[0] = n;
-  f.k[0] = k;
-  f.thr_out[0] = thr_out;
-  f.states = st_full;
-  f.ss = ss;
-  need = (n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
-  capg = (int64_t)sm_count(device) * 2;  // normally exits at once; keep the launch cheap
-  gx = (int)(need < capg ? need : capg);
-  select_pass_kernel<0, MODE_FALLBACK><<<dim3(gx, 1), kSelThreads, 0, stream>>>(f);
-  select_pass_kernel<1, MODE_FALLBACK><<<dim3(gx, 1), kSelThreads, 0, stream>>>(f);
-  select_pass_kernel<2, MODE_FALLBACK><<<dim3(gx, 1), kSelThreads, 0, stream>>>(f);
+static int check_launch(const char* what, int nlaunches) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
-    set_error("sampled select: kernel launch failed: %s", cudaGetErrorString(e));
+    set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
     return ATQ_ECUDA;
   }
-  note_launch(9);
+  note_launch(nlaunches);
   return ATQ_OK;
+}
+
+// plain path: up to kMaxBatch layers per launch sequence; all entries satisfy 0 <= k < n
+static int select_plain_batch(int device, int cnt, const float* const* xs, const int64_t* ns, const int64_t* ks,
+                              float* const* thr_outs, SelectState* states, cudaStream_t stream) {
+  SelectBatch b;
+  memset(&b, 0, sizeof(b));
+  int64_t max_n = 0;
+  for (int i = 0; i < cnt; ++i) {
+    b.x[i] = xs[i]; b.n[i] = ns[i]; b.k[i] = ks[i]; b.thr_out[i] = thr_outs[i];
+    if (ns[i] > max_n) max_n = ns[i];
+  }
+  b.states = states;
+  // CTAs per layer: 16 elements per thread per trip, capped so that the launch is ~8 CTAs per SM
+  int64_t need = (max_n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
+  int64_t cap = ((int64_t)sm_count(device) * 8 + cnt - 1) / cnt;
+  if (cap < 1) cap = 1;
+  int gx = (int)(need < cap ? need : cap);
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)cnt);
+  select_init_kernel<<<cnt, kSelThreads, 0, stream>>>(b);
+  select_pass_kernel<0, MODE_PLAIN><<<grid, kSelThreads, 0, stream>>>(b);
+  select_pass_kernel<1, MODE_PLAIN><<<grid, kSelThreads, 0, stream>>>(b);
+  select_pass_kernel<2, MODE_PLAIN><<<grid, kSelThreads, 0, stream>>>(b);
+  return check_launch("select", 4);
+}
+
+// sampled path: sample -> pivots -> bracket -> filter -> candidate passes (-> full passes on a miss)
+static int select_sampled_batch(int device, int cnt, const float* const* xs, const int64_t* ns, const int64_t* ks,
+                                float* const* thr_outs, SelectState* full_states, SelectState* cand_states,
+                                SampleState* ss, PivotTable* pt, uint32_t* const* cands, const unsigned long long* caps,
+                                cudaStream_t stream) {
+  SelectBatch b;
+  memset(&b, 0, sizeof(b));
+  int64_t max_n = 0;
+  unsigned long long max_cap = 0;
+  for (int i = 0; i < cnt; ++i) {
+    b.x[i] = xs[i]; b.n[i] = ns[i]; b.k[i] = ks[i]; b.thr_out[i] = thr_outs[i]; b.cand[i] = cands[i];
+    if (ns[i] > max_n) max_n = ns[i];
+    if (caps[i] > max_cap) max_cap = caps[i];
+  }
+  b.states = full_states; b.cand_states = cand_states; b.ss = ss; b.pt = pt;
+  const int sms = sm_count(device);
+  // capacities are host-known: write them with the state init (tiny async copy avoided: kernel arg)
+  sample_gather_kernel<<<dim3(kSampleN / 256, cnt), 256, 0, stream>>>(b);
+  sample_pivots_kernel<<<dim3(kPivots / kPivotsPerCta, cnt), 256, 0, stream>>>(b);
+  bracket_kernel<<<cnt, 256, 0, stream>>>(b);
+  {  // filter: ~6 CTAs of 8 warps per SM over the whole batch
+    int64_t need = (max_n + (int64_t)kWarpChunk * 8 * 4 - 1) / ((int64_t)kWarpChunk * 8 * 4);
+    int64_t capg = ((int64_t)sms * 8 + cnt - 1) / cnt;
+    if (capg < 1) capg = 1;
+    if (capg > kFilterMaxCtas) capg = kFilterMaxCtas;
+    int gx = (int)(need < capg ? need : capg);
+    filter_kernel<<<dim3(gx, cnt), kFilterThreads, 0, stream>>>(b);
+  }
+  {
+    SelectBatch c = b;
+    for (int i = 0; i < cnt; ++i) c.n[i] = (long long)caps[i];
+    int64_t need = ((int64_t)max_cap + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
+    int64_t capg = ((int64_t)sms * 4 + cnt - 1) / cnt;
+    if (capg < 1) capg = 1;
+    int gx = (int)(need < capg ? need : capg);
+    // k stays the layer's global rank: pass 0 converts it with count_below
+    select_pass_kernel<0, MODE_CAND><<<dim3(gx, cnt), kSelThreads, 0, stream>>>(c);
+    select_pass_kernel<1, MODE_CAND><<<dim3(gx, cnt), kSelThreads, 0, stream>>>(c);
+    select_pass_kernel<2, MODE_CAND><<<dim3(gx, cnt), kSelThreads, 0, stream>>>(c);
+  }
+  {  // normally every CTA exits at once; keep the launch small
+    int64_t need = (max_n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
+    int64_t capg = ((int64_t)sms * 2 + cnt - 1) / cnt;
+    if (capg < 1) capg = 1;
+    int gx = (int)(need < capg ? need : capg);
+    select_pass_kernel<0, MODE_FALLBACK><<<dim3(gx, cnt), kSelThreads, 0, stream>>>(b);
+    select_pass_kernel<1, MODE_FALLBACK><<<dim3(gx, cnt), kSelThreads, 0, stream>>>(b);
+    select_pass_kernel<2, MODE_FALLBACK><<<dim3(gx, cnt), kSelThreads, 0, stream>>>(b);
+  }
+  return check_launch("sampled select", 10);
+}
+
+// workspace plan shared by the size query and the launcher
+struct WsPlan {
+  size_t plain_states;   // offset of SelectState[count] (plain layers + stats slots)
+  size_t full_states, cand_states, ss, pt, cand;  // offsets of the sampled layers' arrays / first buffer
+  size_t total;
+};
+static WsPlan plan_ws(int count, const int64_t* ns) {
+  WsPlan p;
+  int sampled = 0;
+  size_t cand_bytes = 0;
+  if (ns != nullptr) {
+    const int64_t min_n = sample_min_n(count, ns);
+    for (int i = 0; i < count; ++i)
+      if (ns[i] >= min_n) { ++sampled; cand_bytes += align256((size_t)cand_capacity(ns[i]) * 4); }
+  }
+  size_t off = 0;
+  p.plain_states = off; off += align256(sizeof(SelectState) * (size_t)(count > 0 ? count : 1));
+  p.full_states = off;  off += align256(sizeof(SelectState) * (size_t)sampled);
+  p.cand_states = off;  off += align256(sizeof(SelectState) * (size_t)sampled);
+  p.ss = off;           off += align256(sizeof(SampleState) * (size_t)sampled);
+  p.pt = off;           off += align256(sizeof(PivotTable) * (size_t)sampled);
+  p.cand = off;         off += cand_bytes;
+  p.total = off;
+  return p;
+}
+
+__global__ void set_caps_kernel(SampleState* ss, const unsigned long long c0, const unsigned long long c1,
+                                const unsigned long long c2, const unsigned long long c3, int base, int cnt) {
+  const unsigned long long c[4] = {c0, c1, c2, c3};
+  if ((int)threadIdx.x < cnt) ss[base + threadIdx.x].cap = c[threadIdx.x];
 }
 
 extern "C" {
 
-size_t atq_workspace_bytes_select_kth_abs(int64_t n) {
-  return n >= kSampleMinN ? big_layer_ws(n) : align256(sizeof(SelectState));
-}
+size_t atq_workspace_bytes_adaptive_threshold_batched(int count, const int64_t* ns) { return plan_ws(count, ns).total; }
+size_t atq_workspace_bytes_select_kth_abs(int64_t n) { return plan_ws(1, &n).total; }
+size_t atq_workspace_bytes_adaptive_threshold(int64_t n) { return plan_ws(1, &n).total; }
 
-int atq_select_kth_abs(int device, const float* x, int64_t n, int64_t k, float* thr_out, void* ws, size_t ws_bytes,
-                       atq_stream_t stream) {
-  ATQ_CHECK_ARG(x && thr_out && n > 0, "null pointer or n <= 0");
-  ATQ_CHECK_ARG(k >= 0 && k < n, "k out of range");
-  ATQ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 3u) == 0, "x must be 4-byte aligned");
-  if (ws == nullptr || ws_bytes < atq_workspace_bytes_select_kth_abs(n)) {
-    set_error("atq_select_kth_abs: workspace too small");
+int atq_adaptive_threshold_batched(int device, int count, const float* const* w_ptrs, const int64_t* ns,
+                                   const int64_t* ks, float threshold_factor, float* const* thr_ptrs, void* ws,
+                                   size_t ws_bytes, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(count > 0 && w_ptrs && ns && ks && thr_ptrs, "null pointer or count <= 0");
+  const WsPlan plan = plan_ws(count, ns);
+  if (ws == nullptr || ws_bytes < plan.total) {
+    set_error("atq_adaptive_threshold_batched: workspace too small");
     return ATQ_EWORKSPACE;
   }
   ATQ_ENSURE_DEVICE(device);
-  if (use_sampling(x, n)) return select_sampled_impl(device, x, n, k, thr_out, ws, (cudaStream_t)stream);
-  return select_batched_impl(device, 1, &x, &n, &k, &thr_out, ws, (cudaStream_t)stream);
-}
+  cudaStream_t stream = (cudaStream_t)stream_;
+  char* wsb = reinterpret_cast<char*>(ws);
+  SelectState* plain_states = reinterpret_cast<SelectState*>(wsb + plan.plain_states);
+  SelectState* full_states = reinterpret_cast<SelectState*>(wsb + plan.full_states);
+  SelectState* cand_states = reinterpret_cast<SelectState*>(wsb + plan.cand_states);
+  SampleState* ss = reinterpret_cast<SampleState*>(wsb + plan.ss);
+  PivotTable* pt = reinterpret_cast<PivotTable*>(wsb + plan.pt);
+  char* cand_base = wsb + plan.cand;
 
-size_t atq_workspace_bytes_adaptive_threshold(int64_t n) { return atq_workspace_bytes_adaptive_threshold_batched(1, &n); }
+  // three kinds of layers: edge branches (|W| statistics), small (batched plain radix select),
+  // large and 16-byte aligned (batched sampling front-end)
+  const float* px[kMaxBatch]; int64_t pn[kMaxBatch], pk[kMaxBatch]; float* pthr[kMaxBatch];
+  const float* sx[kMaxBatch]; int64_t sn[kMaxBatch], sk[kMaxBatch]; float* sthr[kMaxBatch];
+  uint32_t* scand[kMaxBatch]; unsigned long long scap[kMaxBatch];
+  int pm = 0, sm = 0, pslot = 0, sslot = 0;
+  size_t cand_off = 0;
+  auto flush_plain = [&]() -> int {
+    if (pm == 0) return ATQ_OK;
+    int r = select_plain_batch(device, pm, px, pn, pk, pthr, plain_states + pslot, stream);
+    pslot += pm; pm = 0;
+    return r;
+  };
+  auto flush_sampled = [&]() -> int {
+    if (sm == 0) return ATQ_OK;
+    for (int i0 = 0; i0 < sm; i0 += 4) {  // capacities -> SampleState.cap (kernel arguments, no host buffer)
+      unsigned long long c[4] = {0, 0, 0, 0};
+      int m = sm - i0 < 4 ? sm - i0 : 4;
+      for (int j = 0; j < m; ++j) c[j] = scap[i0 + j];
+      set_caps_kernel<<<1, 32, 0, stream>>>(ss, c[0], c[1], c[2], c[3], sslot + i0, m);
+    }
+    int r = select_sampled_batch(device, sm, sx, sn, sk, sthr, full_states + sslot, cand_states + sslot, ss + sslot,
+                                 pt + sslot, scand, scap, stream);
+    sslot += sm; sm = 0;
+    return r;
+  };
+  const int64_t min_n = sample_min_n(count, ns);
+  for (int i = 0; i < count; ++i) {
+    ATQ_CHECK_ARG(w_ptrs[i] && thr_ptrs[i] && ns[i] > 0, "null layer pointer or empty layer");
+    ATQ_CHECK_ARG((reinterpret_cast<uintptr_t>(w_ptrs[i]) & 3u) == 0, "weights must be 4-byte aligned");
+    const bool in_range = ks[i] > 0 && ks[i] < ns[i];
+    const bool big = ns[i] >= min_n;
+    if (in_range && big && (reinterpret_cast<uintptr_t>(w_ptrs[i]) & 15u) == 0) {
+      sx[sm] = w_ptrs[i]; sn[sm] = ns[i]; sk[sm] = ks[i]; sthr[sm] = thr_ptrs[i];
+      scap[sm] = cand_capacity(ns[i]);
+      scand[sm] = reinterpret_cast<uint32_t*>(cand_base + cand_off);
+      if (++sm == kMaxBatch) { int r = flush_sampled(); if (r != ATQ_OK) return r; }
+    } else if (in_range) {
+      px[pm] = w_ptrs[i]; pn[pm] = ns[i]; pk[pm] = ks[i]; pthr[pm] = thr_ptrs[i];
+      if (++pm == kMaxBatch) { int r = flush_plain(); if (r != ATQ_OK) return r; }
+    } else {
+      int r = flush_plain();  // keep slot indices in launch order
+      if (r != ATQ_OK) return r;
+      void* stats = plain_states + pslot;  // 16 bytes of this layer's slot
+      ++pslot;
+      r = atq_abs_stats(device, w_ptrs[i], ns[i], stats, nullptr, 0, stream_);
+      if (r != ATQ_OK) return r;
+      threshold_from_stats_kernel<<<1, 1, 0, stream>>>((const AbsStatsView*)stats, (long long)ns[i], ks[i] >= ns[i] ? 1 : 0,
+                                                        threshold_factor, thr_ptrs[i]);
+      ATQ_LAUNCH_CHECK();
+    }
+    if (big) cand_off += align256((size_t)cand_capacity(ns[i]) * 4);
+  }
+  int r = flush_plain();
+  if (r != ATQ_OK) return r;
+  return flush_sampled();
+}
 
 int atq_adaptive_threshold(int device, const float* w, int64_t n, int64_t k, float threshold_factor, float* thr_out,
                            void* ws, size_t ws_bytes, atq_stream_t stream) {
@@ -564,64 +669,24 @@ int atq_adaptive_threshold(int device, const float* w, int64_t n, int64_t k, flo
   return atq_adaptive_threshold_batched(device, 1, xs, &n, &k, threshold_factor, ts, ws, ws_bytes, stream);
 }
 
-size_t atq_workspace_bytes_adaptive_threshold_batched(int count, const int64_t* ns) {
-  // one SelectState slot per layer, then a private region per large (sampled) layer
-  size_t total = align256(sizeof(SelectState)) * (size_t)(count > 0 ? count : 1);
-  if (ns != nullptr)
-    for (int i = 0; i < count; ++i)
-      if (ns[i] >= kSampleMinN) total += big_layer_ws(ns[i]);
-  return total;
-}
-
-int atq_adaptive_threshold_batched(int device, int count, const float* const* w_ptrs, const int64_t* ns,
-                                   const int64_t* ks, float threshold_factor, float* const* thr_ptrs, void* ws,
-                                   size_t ws_bytes, atq_stream_t stream_) {
-  ATQ_CHECK_ARG(count > 0 && w_ptrs && ns && ks && thr_ptrs, "null pointer or count <= 0");
-  if (ws == nullptr || ws_bytes < atq_workspace_bytes_adaptive_threshold_batched(count, ns)) {
-    set_error("atq_adaptive_threshold_batched: workspace too small");
-    return ATQ_EWORKSPACE;
-  }
-  ATQ_ENSURE_DEVICE(device);
-  cudaStream_t stream = (cudaStream_t)stream_;
-  // small in-range layers go through the batched select, large ones through the sampling front-end,
-  // the two edge branches use |W| statistics
-  const float* xs[kMaxBatch];
-  int64_t n2[kMaxBatch], k2[kMaxBatch];
-  float* t2[kMaxBatch];
-  int m = 0, slot = 0;
-  char* wsb = reinterpret_cast<char*>(ws);
-  const size_t st_sz = align256(sizeof(SelectState));
-  size_t big_off = st_sz * (size_t)count;
-  for (int i = 0; i < count; ++i) {
-    ATQ_CHECK_ARG(w_ptrs[i] && thr_ptrs[i] && ns[i] > 0, "null layer pointer or empty layer");
-    ATQ_CHECK_ARG((reinterpret_cast<uintptr_t>(w_ptrs[i]) & 3u) == 0, "weights must be 4-byte aligned");
-    const bool in_range = ks[i] > 0 && ks[i] < ns[i];
-    if (in_range && use_sampling(w_ptrs[i], ns[i])) {
-      int r = select_sampled_impl(device, w_ptrs[i], ns[i], ks[i], thr_ptrs[i], wsb + big_off, stream);
-      if (r != ATQ_OK) return r;
-    } else if (in_range) {
-      xs[m] = w_ptrs[i]; n2[m] = ns[i]; k2[m] = ks[i]; t2[m] = thr_ptrs[i];
-      if (++m == kMaxBatch) {
-        int r = select_batched_impl(device, m, xs, n2, k2, t2, wsb + (size_t)slot * st_sz, stream);
-        if (r != ATQ_OK) return r;
-        slot += m; m = 0;
-      }
-    } else {
-      void* stats = wsb + (size_t)slot * st_sz;  // 16 bytes of this layer's slot
-      ++slot;
-      int r = atq_abs_stats(device, w_ptrs[i], ns[i], stats, nullptr, 0, stream_);
-      if (r != ATQ_OK) return r;
-      threshold_from_stats_kernel<<<1, 1, 0, stream>>>((const AbsStatsView*)stats, (long long)ns[i], ks[i] >= ns[i] ? 1 : 0,
-                                                        threshold_factor, thr_ptrs[i]);
-      ATQ_LAUNCH_CHECK();
+int atq_select_kth_abs(int device, const float* x, int64_t n, int64_t k, float* thr_out, void* ws, size_t ws_bytes,
+                       atq_stream_t stream) {
+  ATQ_CHECK_ARG(x && thr_out && n > 0, "null pointer or n <= 0");
+  ATQ_CHECK_ARG(k >= 0 && k < n, "k out of range");
+  if (k == 0) {
+    // rank 0 is in range for a select but is the "k <= 0" branch of the threshold stage: route it
+    // through the plain path directly
+    ATQ_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 3u) == 0, "x must be 4-byte aligned");
+    if (ws == nullptr || ws_bytes < plan_ws(1, &n).total) {
+      set_error("atq_select_kth_abs: workspace too small");
+      return ATQ_EWORKSPACE;
     }
-    if (ns[i] >= kSampleMinN) big_off += big_layer_ws(ns[i]);
+    ATQ_ENSURE_DEVICE(device);
+    return select_plain_batch(device, 1, &x, &n, &k, &thr_out, reinterpret_cast<SelectState*>(ws), (cudaStream_t)stream);
   }
-  if (m > 0) {
-    int r = select_batched_impl(device, m, xs, n2, k2, t2, wsb + (size_t)slot * st_sz, stream);
-    if (r != ATQ_OK) return r;
-  }
-  return ATQ_OK;
+  const float* const xs[1] = {x};
+  float* const ts[1] = {thr_out};
+  return atq_adaptive_threshold_batched(device, 1, xs, &n, &k, 0.f, ts, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -237,9 +237,12 @@ def test_sampled_select_large_layers_bit_exact(kind):
     assert np.float32(got.item()).tobytes() == np.float32(a.min()).tobytes()
     got = eng.select_kth_abs(wg, n - 1)
     assert np.float32(got.item()).tobytes() == np.float32(a.max()).tobytes()
-    # batched entry point mixes small and large layers
+    # batched entry point mixes small, medium (sampled only because the batch is large) and large layers
     small = _weights((192, 192), 3, "uniform").to(DEV)
-    thr = eng.adaptive_threshold_batched([small, wg, small], [0.3, 0.3, 0.1])
+    medium = wg[: (1 << 22) + 8]
+    thr = eng.adaptive_threshold_batched([small, wg, medium, small], [0.3, 0.3, 0.2, 0.1])
     assert float(thr[1]) == float(eng.adaptive_threshold(wg, 0.3))
     assert float(thr[0]) == float(eng.adaptive_threshold(small, 0.3))
-    assert float(thr[2]) == float(eng.adaptive_threshold(small, 0.1))
+    assert float(thr[3]) == float(eng.adaptive_threshold(small, 0.1))
+    km = int(0.2 * medium.numel())
+    assert np.float32(thr[2].item()).tobytes() == np.float32(np.partition(a[: medium.numel()], km)[km]).tobytes()
