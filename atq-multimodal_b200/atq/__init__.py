@@ -10,7 +10,8 @@ from .quantizers import adaptive_ternary_quantization
 from .layers import TernaryLinear
 from .routing import apply_selective_routing, SelectiveGradientRouting
 from .precision_boost import ResidualPrecisionBoostLinear
-from ._engine import set_gemm_mode, get_gemm_mode, set_ste, set_packed_gemm, prepare_quantization
+from ._engine import (set_gemm_mode, get_gemm_mode, set_ste, set_packed_gemm, prepare_quantization,
+                      notify_weights_changed)
 
 __all__ = [
     'adaptive_ternary_quantization',

@@ -197,6 +197,22 @@ def split_bf16(x2: torch.Tensor, want_lo: bool):
     return hi, lo, pitch
 
 
+def split_bf16_colsum(x2: torch.Tensor, want_lo: bool):
+    """split_bf16 of a contiguous [rows, cols] tensor fused with its column sums (bias gradient).
+    Falls back to the two separate kernels when the fused path's layout conditions do not hold."""
+    rows, cols = x2.shape
+    if cols % 8 != 0 or x2.stride(0) != cols or x2.data_ptr() % 16 != 0:
+        return split_bf16(x2, want_lo), colsum(x2)
+    dev = nv.device_index(x2)
+    hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=x2.device)
+    lo = torch.empty((rows, cols), dtype=torch.bfloat16, device=x2.device) if want_lo else None
+    out = torch.empty(cols, dtype=torch.float32, device=x2.device)
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_split_colsum(rows, cols), x2.device)
+    nv.call("atq_split_bf16_colsum", dev, x2.data_ptr(), rows, cols, hi.data_ptr(), nv.ptr(lo), out.data_ptr(),
+            ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+    return (hi, lo, cols), out
+
+
 def split_bf16_t(x2: torch.Tensor, want_lo: bool):
     """fp32 [rows, cols] -> transposed (hi_t, lo_t|None, pitch_t), each [cols, pitch_t]."""
     rows, cols = x2.shape
@@ -282,8 +298,32 @@ class LayerOperands:
         self.w_t = None    # (hi, lo|None, pitch_t) [K, pitch_t] dX B operand (None when packed_t is used)
 
 
+# Fused / foreach optimizer kernels (torch.optim.AdamW(fused=True), capturable paths) update parameters
+# without bumping Tensor._version, so the version alone cannot prove that cached operands are current.
+# A global post-step hook counts optimizer steps; any step anywhere invalidates every layer's cache.
+_OPT_STEPS = 0
+
+
+def _count_optimizer_step(optimizer, args, kwargs):
+    global _OPT_STEPS
+    _OPT_STEPS += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook
+    _register_post_hook(_count_optimizer_step)
+except ImportError:  # pragma: no cover - older torch: fall back to versions only
+    pass
+
+
+def notify_weights_changed() -> None:
+    """Call after mutating parameters behind autograd's back (e.g. through `.data`)."""
+    global _OPT_STEPS
+    _OPT_STEPS += 1
+
+
 def _key(weight, alpha, mask, sparsity_target, threshold_factor):
-    return (weight.data_ptr(), weight._version, tuple(weight.shape),
+    return (_OPT_STEPS, weight.data_ptr(), weight._version, tuple(weight.shape),
             None if alpha is None else (alpha.data_ptr(), alpha._version),
             None if mask is None else (mask.data_ptr(), mask._version),
             float(sparsity_target), float(threshold_factor), _MODE)
@@ -313,7 +353,7 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
         # TernaryLinear: the GEMMs read the 2-bit codec bytes directly whenever the contraction
         # dimension allows 16-byte codec rows per k-block; bf16 copies only for odd shapes
         hi = torch.empty((M, pitch), dtype=bf, device=w.device)
-        hi_t = torch.empty((K, pitch_t), dtype=bf, device=w.device)
+        hi_t = None  # dX reads `hi` in place through MN-major descriptors
         if M % 64 == 0:
             packed_t = torch.empty(n // 4, dtype=torch.uint8, device=w.device)
         lo = lo_t = None
@@ -322,19 +362,17 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
     else:
         want_lo = _use_lo()
         hi = torch.empty((M, pitch), dtype=bf, device=w.device)
-        hi_t = torch.empty((K, pitch_t), dtype=bf, device=w.device)
         lo = torch.empty((M, pitch), dtype=bf, device=w.device) if want_lo else None
-        lo_t = torch.empty((K, pitch_t), dtype=bf, device=w.device) if want_lo else None
+        hi_t = lo_t = None  # dX reads hi/lo in place through MN-major descriptors
         mk = nv.require_f32(mask, "precision_mask")
         al = nv.require_f32(alpha.detach(), "alpha")
         nv.call("atq_build_mixed_operands", dev, w.data_ptr(), mk.data_ptr(), M, K, thr.data_ptr(), al.data_ptr(),
-                packed.data_ptr() if flat_ok else None, hi.data_ptr(), nv.ptr(lo), pitch, hi_t.data_ptr(),
-                nv.ptr(lo_t), pitch_t, st)
+                packed.data_ptr() if flat_ok else None, hi.data_ptr(), nv.ptr(lo), pitch, None, None, pitch_t, st)
     if not flat_ok:  # rows of the flat codec do not start on byte boundaries
         nv.call("atq_ternarize_pack2", dev, w.data_ptr(), n, thr.data_ptr(), packed.data_ptr(), None, st)
     cache.key, cache.thr, cache.packed, cache.packed_t = key, thr, packed, packed_t
-    cache.w = None if hi is None else (hi, lo, pitch)
-    cache.w_t = None if hi_t is None else (hi_t, lo_t, pitch_t)
+    cache.w = (hi, lo, pitch)           # [M, pitch]: forward B operand (K-major) ...
+    cache.w_t = (hi, lo, pitch, 1)      # ... and, read as MN-major, the dX B operand (no transposed copy)
     return cache
 
 
@@ -405,17 +443,19 @@ class _TernaryLinearFn(torch.autograd.Function):
             g2 = g2.contiguous()
         if N == 0:
             return (gy.new_zeros(ctx.xshape), None, al.new_zeros(1), g2.new_zeros(M) if ctx.has_bias else None, None)
-        ga = split_bf16(g2, _use_lo())
+        if ctx.has_bias:
+            ga, dbias = split_bf16_colsum(g2, _use_lo())  # one pass over dY: operand split + bias gradient
+        else:
+            ga, dbias = split_bf16(g2, _use_lo()), None
         # dX = alpha * (dY . T);  d(alpha) = sum((dY . T) .* X) fused in the same epilogue
         if _want_packed(N) and packed_gemm_ok(M, ctx.packed_t):
             dx, dalpha = tgemm_packed(ga, ctx.packed_t, N, K, M, scale=al, dot_ref=x2)
         else:
             dx, dalpha = tgemm(ga, ctx.ops_w_t, N, K, M, scale=al, dot_ref=x2)
-        dbias = colsum(g2) if ctx.has_bias else None
         dw = None
-        if ctx.ste:  # opt-in straight-through estimator: dW = G
-            gt, xt = split_bf16_t(g2, _use_lo()), split_bf16_t(x2, _use_lo())
-            dw, _ = tgemm_dw_masked(gt, xt, M, K, N)
+        if ctx.ste:  # opt-in straight-through estimator: dW = G (dY and X consumed MN-major, no transposes)
+            xa = split_bf16(x2, _use_lo())
+            dw, _ = tgemm_dw_masked(ga + (1,), xa + (1,), M, K, N)
         return dx.reshape(ctx.xshape), dw, dalpha, dbias, None
 
 
@@ -434,7 +474,16 @@ class _RPBLinearFn(torch.autograd.Function):
         else:
             xa = split_bf16(x2, _use_lo())
             y, _ = tgemm(xa, ops.w, N, M, K, scale=None, bias=None if bias is None else bias.detach())
-        ctx.save_for_backward(x2, mask)
+        # backward consumes the SAME bf16 hi/lo split of x (MN-major, as the dW B operand): save it
+        # instead of the fp32 activations (same bytes), so nothing is split or transposed twice
+        if N == 0:
+            ctx.save_for_backward(x2, mask)
+        elif xa[1] is None:
+            ctx.save_for_backward(xa[0], mask)
+        else:
+            ctx.save_for_backward(xa[0], xa[1], mask)
+        ctx.x_pitch = xa[2] if N else 0
+        ctx.n_tokens = N
         ctx.ops_w_t, ctx.packed = ops.w_t, ops.packed
         ctx.has_bias = bias is not None
         ctx.wshape = (M, K)
@@ -443,26 +492,29 @@ class _RPBLinearFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        x2, mask = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        mask = saved[-1]
         M, K = ctx.wshape
-        N = x2.shape[0]
+        N = ctx.n_tokens
         g2 = nv.require_f32(gy, "grad_output").reshape(-1, M)
         if not g2.is_contiguous():
             g2 = g2.contiguous()
         if N == 0:
             z = g2.new_zeros
             return (gy.new_zeros(ctx.xshape), z((M, K)), z(1), z(M) if ctx.has_bias else None, None, None)
-        lo = _use_lo()
+        xa = (saved[0], saved[1] if len(saved) == 3 else None, ctx.x_pitch)
+        if ctx.has_bias:  # ONE pass over dY: the split feeds both backward GEMMs, the column sums are d(bias)
+            ga, dbias = split_bf16_colsum(g2, xa[1] is not None)
+        else:
+            ga, dbias = split_bf16(g2, xa[1] is not None), None
         dx = None
         if ctx.needs_input_grad[0]:
-            ga = split_bf16(g2, lo)
-            dx, _ = tgemm(ga, ctx.ops_w_t, N, K, M)
+            dx, _ = tgemm(ga, ctx.ops_w_t, N, K, M)   # B = Wm [M, K] read MN-major
             dx = dx.reshape(ctx.xshape)
-        # G = dY^T X with the mask and the d(alpha) reduction fused into the epilogue
-        gt, xt = split_bf16_t(g2, lo), split_bf16_t(x2, lo)
+        # G = dY^T X with the mask and the d(alpha) reduction fused into the epilogue; dY [N, M] and
+        # X [N, K] are consumed in place as MN-major operands
         mk = mask if mask.is_contiguous() else mask.contiguous()
-        dw, dalpha = tgemm_dw_masked(gt, xt, M, K, N, mask=mk, packed=ctx.packed)
-        dbias = colsum(g2) if ctx.has_bias else None
+        dw, dalpha = tgemm_dw_masked(ga + (1,), xa + (1,), M, K, N, mask=mk, packed=ctx.packed)
         return dx, dw, dalpha, dbias, None, None
 
 

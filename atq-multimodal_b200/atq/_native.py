@@ -21,11 +21,11 @@ if not os.path.exists(_LIB_PATH):
         "(or `make -C atq-multimodal_b200/csrc`). The atq package has no CPU or eager fallback.")
 _lib = ctypes.CDLL(_LIB_PATH)
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class BF16Operand(Structure):
-    _fields_ = [("hi", c_void_p), ("lo", c_void_p), ("pitch", c_int64)]
+    _fields_ = [("hi", c_void_p), ("lo", c_void_p), ("pitch", c_int64), ("mn_major", c_int32), ("reserved", c_int32)]
 
 
 _P = c_void_p
@@ -53,6 +53,8 @@ _SIGS = {
     "atq_unpack2_to_i8": (c_int, [c_int, _P, c_int64, _P, _P]),
     "atq_route_mask_mul": (c_int, [c_int, _P, _P, _P, c_int64, _P, _P]),
     "atq_split_bf16": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
+    "atq_workspace_bytes_split_colsum": (c_size_t, [c_int64, c_int64]),
+    "atq_split_bf16_colsum": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "atq_split_bf16_t": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P]),
     "atq_build_ternary_operands": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P]),
     "atq_build_mixed_operands": (c_int, [c_int, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P,
@@ -146,5 +148,6 @@ def call(name: str, *args) -> None:
     check(getattr(_lib, name)(*args), name)
 
 
-def operand(hi: torch.Tensor, lo, pitch: int) -> BF16Operand:
-    return BF16Operand(hi.data_ptr(), None if lo is None else lo.data_ptr(), pitch)
+def operand(hi: torch.Tensor, lo, pitch: int, mn_major: int = 0) -> BF16Operand:
+    """mn_major=1: the tensor is [kdim, rows] row-major (a row-major activation/weight used transposed)."""
+    return BF16Operand(hi.data_ptr(), None if lo is None else lo.data_ptr(), pitch, int(mn_major), 0)

@@ -121,11 +121,30 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor_sw128(uint32_t saddr) 
   return d;
 }
 
-// instruction descriptor: kind::f16, A=B=bf16, D=f32, both K-major, M=128, N=BLOCK_N
-template <int BLOCK_N>
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// shared-memory matrix descriptor: MN-major, SWIZZLE_128B.  The tile is a row of [64 k x 64 mn] blocks
+// (each 64 rows of 128 B, exactly what one TMA box of a row-major [k, mn] tensor delivers): 64-element
+// MN groups are 8192 B apart (leading byte offset), 8-row K groups 1024 B apart (stride byte offset).
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;  // leading byte offset: next 64 MN elements
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: next 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
+
+// instruction descriptor: kind::f16, A=B=bf16, D=f32, M=128, N=BLOCK_N; bit 15 / 16 = A / B is MN-major
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+         ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// operand layouts: 0 = A,B K-major ([rows|cols, k] row-major: forward), 1 = B MN-major (memory is
+// [k, cols] row-major: dX straight from the [out, in] weight copy), 2 = A and B MN-major (memory is
+// [k, rows] and [k, cols]: dW straight from dY [tokens, out] and X [tokens, in], no transposes)
+enum { LAYOUT_KK = 0, LAYOUT_KM = 1, LAYOUT_MM = 2 };
 
 // ------------------------------------------------------------------------------------------
 // 2-bit codec -> bf16 in registers.  One 32-bit word holds 16 codes (code i at bits 2i..2i+1,
@@ -200,13 +219,15 @@ struct GemmCfg {
 // (column tile fastest, so the CTAs working at the same time share A tiles through L2 and the
 // whole B operand stays L2-resident).  The accumulator is double-buffered in TMEM: the MMA warp
 // starts tile i+1 while the epilogue warps drain tile i.
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false>
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK>
 __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     tgemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const GemmParams p) {
   using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
+  constexpr bool A_MN = (LAYOUT == LAYOUT_MM), B_MN = (LAYOUT != LAYOUT_KK);
+  static_assert(!(B_PACKED && LAYOUT != LAYOUT_KK), "packed B is K-major");
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -264,12 +285,28 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           mbar_expect_tx(full_bar(stage), B_PACKED ? NUM_A * Cfg::kABytes : Cfg::kStageBytes);
           const int32_t kc = kb * BLOCK_K;
-          tma_load_2d(sa, &map_a_hi, kc, m0, full_bar(stage));
-          if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes, &map_a_lo, kc, m0, full_bar(stage));
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &map_a_hi, kc, m0, full_bar(stage));
+            if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes, &map_a_lo, kc, m0, full_bar(stage));
+          } else {  // [64 k x 64 mn] boxes of the row-major [k, rows] tensor
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j) {
+              tma_load_2d(sa + j * 8192, &map_a_hi, m0 + 64 * j, kc, full_bar(stage));
+              if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes + j * 8192, &map_a_lo, m0 + 64 * j, kc, full_bar(stage));
+            }
+          }
           if constexpr (!B_PACKED) {
             const uint32_t sb = sa + NUM_A * Cfg::kABytes;
-            tma_load_2d(sb, &map_b_hi, kc, n0, full_bar(stage));
-            if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, n0, full_bar(stage));
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &map_b_hi, kc, n0, full_bar(stage));
+              if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, n0, full_bar(stage));
+            } else {
+#pragma unroll
+              for (int j = 0; j < (BLOCK_N + 63) / 64; ++j) {
+                tma_load_2d(sb + j * 8192, &map_b_hi, n0 + 64 * j, kc, full_bar(stage));
+                if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes + j * 8192, &map_b_lo, n0 + 64 * j, kc, full_bar(stage));
+              }
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -278,7 +315,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
   } else if (warp_idx == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BLOCK_N>();
+      constexpr uint32_t idesc = make_idesc<BLOCK_N, A_MN, B_MN>();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -294,17 +331,20 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + NUM_A * Cfg::kABytes;
-          const uint64_t da_hi = make_smem_desc_kmajor_sw128(sa);
-          const uint64_t da_lo = make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
-          const uint64_t db_hi = make_smem_desc_kmajor_sw128(sb);
-          const uint64_t db_lo = make_smem_desc_kmajor_sw128(sb + Cfg::kBBytes);
+          const uint64_t da_hi = A_MN ? make_smem_desc_mnmajor_sw128(sa) : make_smem_desc_kmajor_sw128(sa);
+          const uint64_t da_lo = A_MN ? make_smem_desc_mnmajor_sw128(sa + Cfg::kABytes) : make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
+          const uint64_t db_hi = B_MN ? make_smem_desc_mnmajor_sw128(sb) : make_smem_desc_kmajor_sw128(sb);
+          const uint64_t db_lo = B_MN ? make_smem_desc_mnmajor_sw128(sb + Cfg::kBBytes) : make_smem_desc_kmajor_sw128(sb + Cfg::kBBytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);  // 32 B per K step, in 16 B units
-            umma_bf16(tmem_acc, da_hi + koff, db_hi + koff, idesc, accumulate);
+            // one K step (16 elements): 32 B inside the swizzled row when K-major, 16 rows of 128 B
+            // when MN-major; in 16-byte units
+            const uint64_t koa = (uint64_t)(A_MN ? (k * UMMA_K * 128) >> 4 : (k * UMMA_K * 2) >> 4);
+            const uint64_t kob = (uint64_t)(B_MN ? (k * UMMA_K * 128) >> 4 : (k * UMMA_K * 2) >> 4);
+            umma_bf16(tmem_acc, da_hi + koa, db_hi + kob, idesc, accumulate);
             accumulate = 1;
-            if (NUM_A == 2) umma_bf16(tmem_acc, da_lo + koff, db_hi + koff, idesc, 1u);
-            if (NUM_B == 2) umma_bf16(tmem_acc, da_hi + koff, db_lo + koff, idesc, 1u);
+            if (NUM_A == 2) umma_bf16(tmem_acc, da_lo + koa, db_hi + kob, idesc, 1u);
+            if (NUM_B == 2) umma_bf16(tmem_acc, da_hi + koa, db_lo + kob, idesc, 1u);
           }
           umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -508,22 +548,50 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
   return ATQ_OK;
 }
 
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false>
+// bf16 [kdim, mn] row-major with pitch (MN-major operand); box = [64 mn, 64 k]
+static int make_map_mn(CUtensorMap* map, const uint16_t* ptr, int64_t mn, int64_t kdim, int64_t pitch) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return ATQ_ECUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)mn, (cuuint64_t)kdim};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BLOCK_K};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (MN-major) failed (%d) mn=%lld kdim=%lld pitch=%lld ptr=%p", (int)r, (long long)mn,
+              (long long)kdim, (long long)pitch, (const void*)ptr);
+    return ATQ_ECUDA;
+  }
+  return ATQ_OK;
+}
+
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK>
 static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
   using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
-  if ((r = make_map(&ma_hi, a->hi, p.rows, p.kdim, a->pitch, BLOCK_M)) != ATQ_OK) return r;
+  constexpr bool A_MN = (LAYOUT == LAYOUT_MM), B_MN = (LAYOUT != LAYOUT_KK);
+  auto map_a = [&](CUtensorMap* m, const uint16_t* ptr) {
+    return A_MN ? make_map_mn(m, ptr, p.rows, p.kdim, a->pitch) : make_map(m, ptr, p.rows, p.kdim, a->pitch, BLOCK_M);
+  };
+  auto map_b = [&](CUtensorMap* m, const uint16_t* ptr) {
+    return B_MN ? make_map_mn(m, ptr, p.cols, p.kdim, b->pitch) : make_map(m, ptr, p.cols, p.kdim, b->pitch, BLOCK_N);
+  };
+  if ((r = map_a(&ma_hi, a->hi)) != ATQ_OK) return r;
   if constexpr (!B_PACKED) {
-    if ((r = make_map(&mb_hi, b->hi, p.cols, p.kdim, b->pitch, BLOCK_N)) != ATQ_OK) return r;
+    if ((r = map_b(&mb_hi, b->hi)) != ATQ_OK) return r;
   } else {
     mb_hi = ma_hi;  // unused by the packed-B kernel
   }
   ma_lo = ma_hi;
   mb_lo = mb_hi;
-  if (NUM_A == 2 && (r = make_map(&ma_lo, a->lo, p.rows, p.kdim, a->pitch, BLOCK_M)) != ATQ_OK) return r;
-  if (NUM_B == 2 && (r = make_map(&mb_lo, b->lo, p.cols, p.kdim, b->pitch, BLOCK_N)) != ATQ_OK) return r;
-  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED>;
+  if (NUM_A == 2 && (r = map_a(&ma_lo, a->lo)) != ATQ_OK) return r;
+  if (NUM_B == 2 && (r = map_b(&mb_lo, b->lo)) != ATQ_OK) return r;
+  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED, LAYOUT>;
   static bool attr_done_dev[64] = {false};  // per instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -554,13 +622,13 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
   return ATQ_OK;
 }
 
-template <int EPI>
-static int dispatch(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
+template <int EPI, int LAYOUT>
+static int dispatch_layout(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
   const bool a2 = a->lo != nullptr, b2 = b->lo != nullptr;
   // tile width: 256 columns when the pipeline still has >= 3 stages, else 128; narrow outputs use 64/128
   const bool narrow = p.cols <= 64;
   const bool mid = p.cols <= 128;
-#define ATQ_GO(NA, NB, BN) return launch_cfg<NA, NB, BN, EPI>(a, b, p, stream, grid_used)
+#define ATQ_GO(NA, NB, BN) return launch_cfg<NA, NB, BN, EPI, false, LAYOUT>(a, b, p, stream, grid_used)
   if (narrow) {
     if (a2 && b2) ATQ_GO(2, 2, 64);
     if (a2) ATQ_GO(2, 1, 64);
@@ -576,6 +644,16 @@ static int dispatch(const atq_bf16_operand* a, const atq_bf16_operand* b, const 
   if (a2) ATQ_GO(2, 1, 256);
   ATQ_GO(1, 1, 256);
 #undef ATQ_GO
+}
+
+template <int EPI>
+static int dispatch(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
+  const bool amn = a->mn_major != 0, bmn = b->mn_major != 0;
+  if (!amn && !bmn) return dispatch_layout<EPI, LAYOUT_KK>(a, b, p, stream, grid_used);
+  if (!amn && bmn) return dispatch_layout<EPI, LAYOUT_KM>(a, b, p, stream, grid_used);
+  if (amn && bmn) return dispatch_layout<EPI, LAYOUT_MM>(a, b, p, stream, grid_used);
+  set_error("tgemm: A MN-major with B K-major is not built");
+  return ATQ_EINVAL;
 }
 
 static int check_operand(const atq_bf16_operand* o, const char* name) {
@@ -611,7 +689,8 @@ int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf
   int r;
   if ((r = check_operand(a, "a")) != ATQ_OK) return r;
   if ((r = check_operand(b, "b")) != ATQ_OK) return r;
-  ATQ_CHECK_ARG(a->pitch >= kdim && b->pitch >= kdim, "operand pitch smaller than kdim");
+  ATQ_CHECK_ARG(a->pitch >= (a->mn_major ? rows : kdim) && b->pitch >= (b->mn_major ? cols : kdim),
+                "operand pitch smaller than its contiguous extent");
   ATQ_CHECK_ARG((dot_ref == nullptr) == (dot_out == nullptr), "dot_ref and dot_out go together");
   if (dot_out != nullptr && (ws == nullptr || ws_bytes < atq_workspace_bytes_tgemm(rows, cols))) {
     set_error("atq_tgemm: workspace too small");
@@ -700,7 +779,8 @@ int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, i
   int r;
   if ((r = check_operand(dy_t, "dy_t")) != ATQ_OK) return r;
   if ((r = check_operand(x_t, "x_t")) != ATQ_OK) return r;
-  ATQ_CHECK_ARG(dy_t->pitch >= n_tokens && x_t->pitch >= n_tokens, "operand pitch smaller than n_tokens");
+  ATQ_CHECK_ARG(dy_t->pitch >= (dy_t->mn_major ? out_features : n_tokens) && x_t->pitch >= (x_t->mn_major ? in_features : n_tokens),
+                "operand pitch smaller than its contiguous extent");
   ATQ_CHECK_ARG((packed_t == nullptr) == (dalpha_out == nullptr), "packed_t and dalpha_out go together");
   if (dalpha_out != nullptr && (ws == nullptr || ws_bytes < atq_workspace_bytes_tgemm(out_features, in_features))) {
     set_error("atq_tgemm_dw_masked: workspace too small");

@@ -315,6 +315,42 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// split + column sums in one pass over dY (bias gradient rides along): thread (cg, rl) owns column
+// group cg (4 columns) and walks rows rl, rl+R, ...; its four running sums go to part[rl][4cg..],
+// which colsum_stage2_kernel reduces in fixed order (deterministic).  Requires cols % 4 == 0,
+// ld_in == cols == pitch and 16-byte aligned pointers (the flat-path conditions).
+template <bool HAS_LO>
+__global__ void __launch_bounds__(kThreads)
+    split_colsum_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, uint16_t* __restrict__ hi,
+                        uint16_t* __restrict__ lo, float* __restrict__ part, int64_t R) {
+  const int64_t cg4 = cols >> 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cg4 * R) return;
+  const int64_t cg = t % cg4, rl = t / cg4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r0 = rl; r0 < rows; r0 += R * kUnroll) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      const int64_t r = r0 + j * R;
+      if (r < rows) v[j] = ldg_stream4(x + r * cols + 4 * cg);
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      const int64_t r = r0 + j * R;
+      if (r >= rows) continue;
+      const int64_t g = r * cg4 + cg;
+      uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(v[j].x, h0, l0); split_bf16(v[j].y, h1, l1); split_bf16(v[j].z, h2, l2); split_bf16(v[j].w, h3, l3);
+      *reinterpret_cast<uint2*>(hi + 4 * g) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+      if constexpr (HAS_LO)
+        *reinterpret_cast<uint2*>(lo + 4 * g) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+      acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w;
+    }
+  }
+  *reinterpret_cast<float4*>(part + rl * cols + 4 * cg) = acc;
+}
+
 template <bool HAS_LO>
 __global__ void __launch_bounds__(kThreads)
     split_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
@@ -498,11 +534,30 @@ __global__ void __launch_bounds__(256)
 }
 __global__ void __launch_bounds__(256)
     colsum_stage2_kernel(const float* __restrict__ part, int64_t nparts, int64_t cols, float* __restrict__ out) {
-  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float t = 0.f;
-  for (int64_t p = 0; p < nparts; ++p) t += part[p * cols + c];
-  out[c] = t;
+  // CTA = 32 columns; its 8 warps take interleaved partial rows (4 loads in flight each), fixed-order
+  // shared-memory combine: deterministic and no long serial chain
+  __shared__ float s[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < cols) {
+    int64_t p = wid;
+    for (; p + 24 < nparts; p += 32) {
+      a0 += part[p * cols + c];
+      a1 += part[(p + 8) * cols + c];
+      a2 += part[(p + 16) * cols + c];
+      a3 += part[(p + 24) * cols + c];
+    }
+    for (; p < nparts; p += 8) a0 += part[p * cols + c];
+  }
+  s[wid][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (wid == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s[i][lane];
+    out[c] = t;
+  }
 }
 
 // small-N path: one CTA per 32 columns walks every row (single launch, deterministic)
@@ -714,6 +769,47 @@ int atq_build_mixed_operands(int device, const float* w, const float* mask, int6
   return ATQ_OK;
 }
 
+static inline int64_t split_colsum_lanes(int device, int64_t rows, int64_t cols) {
+  int64_t cg4 = cols >> 2;
+  int64_t R = ((int64_t)sm_count(device) * 8 * kThreads) / (cg4 > 0 ? cg4 : 1);
+  if (R > (rows + 3) / 4) R = (rows + 3) / 4;  // at least ~4 rows per lane
+  if (R > 512) R = 512;                        // keeps the second stage short
+  if (R < 1) R = 1;
+  return R;
+}
+
+size_t atq_workspace_bytes_split_colsum(int64_t rows, int64_t cols) {
+  // upper bound over devices: the lane count never exceeds rows
+  int64_t R = (rows + 3) / 4;
+  int64_t cap = ((int64_t)256 * 8 * kThreads) / ((cols >> 2) > 0 ? (cols >> 2) : 1);
+  if (R > cap) R = cap;
+  if (R > 512) R = 512;
+  if (R < 1) R = 1;
+  return (size_t)(R * cols * sizeof(float));
+}
+
+int atq_split_bf16_colsum(int device, const float* x, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo,
+                          float* colsum_out, void* ws, size_t ws_bytes, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && hi && colsum_out && rows > 0 && cols > 0, "null pointer or empty shape");
+  ATQ_CHECK_ARG((cols % 8) == 0 && aligned16(x) && aligned16(hi) && (lo == nullptr || aligned16(lo)),
+                "needs cols % 8 == 0 and 16-byte aligned contiguous tensors");
+  ATQ_ENSURE_DEVICE(device);
+  const int64_t R = split_colsum_lanes(device, rows, cols);
+  if (ws == nullptr || ws_bytes < (size_t)(R * cols * sizeof(float))) {
+    set_error("atq_split_bf16_colsum: workspace too small");
+    return ATQ_EWORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t threads = (cols >> 2) * R;
+  const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
+  if (lo) split_colsum_kernel<true><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R);
+  else split_colsum_kernel<false><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R);
+  ATQ_LAUNCH_CHECK();
+  colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>((const float*)ws, R, cols, colsum_out);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
 size_t atq_workspace_bytes_colsum(int64_t rows, int64_t cols) {
   const int rpc = colsum_rows_per_cta(rows);
   int64_t parts = (rows + rpc - 1) / rpc;
@@ -740,7 +836,7 @@ int atq_colsum_f32(int device, const float* x, int64_t rows, int64_t cols, int64
   ATQ_CHECK_ARG(parts <= 65535, "rows too large for one launch");
   colsum_stage1_kernel<<<g1, 256, 0, stream>>>(x, rows, cols, ld, (float*)ws, rpc);
   ATQ_LAUNCH_CHECK();
-  colsum_stage2_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>((const float*)ws, parts, cols, out);
+  colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>((const float*)ws, parts, cols, out);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }

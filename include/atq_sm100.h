@@ -110,6 +110,12 @@ int atq_route_mask_mul(int device, const float* x, const float* grad_out, const 
  * [rows, pitch]; pitch % 8 == 0, pitch >= cols; padding columns are left untouched. */
 int atq_split_bf16(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in,
                    uint16_t* hi, uint16_t* lo, int64_t pitch, atq_stream_t stream);
+/* split of a contiguous [rows, cols] tensor (cols % 8 == 0) fused with its column sums
+ * (colsum_out[c] = sum_r x[r,c], deterministic two-stage): one pass over dY yields the GEMM
+ * operand and the bias gradient. */
+size_t atq_workspace_bytes_split_colsum(int64_t rows, int64_t cols);
+int atq_split_bf16_colsum(int device, const float* x, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo,
+                          float* colsum_out, void* ws, size_t ws_bytes, atq_stream_t stream);
 /* same, transposed output: hi_t/lo_t are [cols, pitch_t], pitch_t % 8 == 0, pitch_t >= rows.
  * colsum is reserved (must be NULL; use atq_colsum_f32). */
 int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in,
@@ -133,13 +139,19 @@ int atq_build_mixed_operands(int device, const float* w, const float* mask, int6
                              uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, atq_stream_t stream);
 
 /* ---- ternary GEMMs (tcgen05 / TMEM / TMA) -------------------------------------------- */
-/* Common operand description: a bf16 matrix [rows, kdim] with row pitch `pitch` elements
- * (pitch % 8 == 0, base 16-byte aligned), given as hi (+ optional lo) so that the fp32
- * value is hi + lo.  */
+/* Common operand description: a bf16 matrix given as hi (+ optional lo) so that the fp32 value
+ * is hi + lo; pitch % 8 == 0 elements, base 16-byte aligned.
+ *   mn_major == 0: memory is [rows, kdim] row-major (contraction index contiguous, "K-major")
+ *   mn_major == 1: memory is [kdim, rows] row-major (the transposed view of a row-major tensor is
+ *                  consumed in place through MN-major UMMA descriptors: dX reads the [out, in]
+ *                  weight copy, dW reads dY [tokens, out] and X [tokens, in] - no transposes)
+ * Supported combinations (A, B): (0,0), (0,1), (1,1).  */
 typedef struct {
   const uint16_t* hi;
   const uint16_t* lo; /* nullable */
   int64_t pitch;
+  int32_t mn_major;
+  int32_t reserved;
 } atq_bf16_operand;
 
 /* K7 forward:  Y[N,M] = scale * (X[N,K] . B[M,K]^T) + bias      (atq/layers.py:43,

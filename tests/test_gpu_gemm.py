@@ -283,3 +283,53 @@ def test_ternary_linear_packed_policy(policy):
     assert torch.allclose(xg.grad.cpu(), xr.grad, **TOL)
     assert torch.allclose(mod.alpha.grad.cpu(), ref.alpha.grad, rtol=1e-2, atol=1e-1)
     assert mod.weight.grad is None
+
+
+@pytest.mark.parametrize("rows,cols,k", [(128, 128, 64), (300, 200, 136), (16, 1, 96), (800, 192, 192), (192, 384, 800),
+                                         (257, 10, 128), (96, 192, 16), (1000, 520, 1064), (4096, 4096, 1024)])
+def test_tgemm_mn_major_operands(rows, cols, k):
+    """dX reads B as [k, cols] row-major, dW reads A as [k, rows] and B as [k, cols] row-major (MN-major UMMA
+    descriptors, no transposes): same result as the K-major path on explicitly transposed copies."""
+    g = torch.Generator().manual_seed(rows * 3 + cols + k)
+    a = torch.randn(rows, k, generator=g)
+    b = torch.randn(cols, k, generator=g) / k ** 0.5
+    ref = _gemm_ref(a, b)
+    a_k = eng.split_bf16(a.to(DEV), True)                       # [rows, k]  K-major
+    a_mn = eng.split_bf16(a.t().contiguous().to(DEV), True)     # [k, rows]  MN-major memory
+    b_k = eng.split_bf16(b.to(DEV), True)
+    b_mn = eng.split_bf16(b.t().contiguous().to(DEV), True)     # [k, cols]
+    y_kk, _ = eng.tgemm(a_k, b_k, rows, cols, k)
+    y_km, _ = eng.tgemm(a_k, b_mn + (1,), rows, cols, k)
+    assert torch.allclose(y_km.cpu().double(), ref, rtol=1e-3, atol=1e-4), (y_km.cpu().double() - ref).abs().max()
+    assert torch.allclose(y_km, y_kk, rtol=1e-5, atol=1e-5)
+    mask = (torch.rand(rows, cols, generator=g) < 0.3).float().to(DEV)
+    y_mm, _ = eng.tgemm_dw_masked(a_mn + (1,), b_mn + (1,), rows, cols, k, mask=mask)
+    assert torch.allclose(y_mm.cpu().double(), ref * mask.cpu().double(), rtol=1e-3, atol=1e-4)
+    # single-term variants
+    y1, _ = eng.tgemm((a_k[0], None, a_k[2]), (b_mn[0], None, b_mn[2], 1), rows, cols, k)
+    want1 = _gemm_ref(a_k[0][:, :k].float().cpu(), b_mn[0][:, :cols].float().cpu().t())
+    assert torch.allclose(y1.cpu().double(), want1, rtol=1e-4, atol=1e-3)
+    y2, _ = eng.tgemm_dw_masked((a_mn[0], None, a_mn[2], 1), (b_mn[0], None, b_mn[2], 1), rows, cols, k)
+    want2 = _gemm_ref(a_mn[0][:, :rows].float().cpu().t(), b_mn[0][:, :cols].float().cpu().t())
+    assert torch.allclose(y2.cpu().double(), want2, rtol=1e-4, atol=1e-3)
+
+
+def test_fused_optimizer_step_invalidates_cache():
+    """torch's fused AdamW updates weights without bumping Tensor._version; the optimizer post-step
+    hook must still force re-quantization on the next forward."""
+    torch.manual_seed(9)
+    ref = O.OracleRPBLinear(128, 64, 0.1, True, 0.2)
+    mod = atq.ResidualPrecisionBoostLinear(128, 64, 0.1, True, 0.2)
+    mod.load_state_dict(ref.state_dict())
+    mod.to(DEV)
+    o_r = torch.optim.AdamW(ref.parameters(), lr=5e-2, weight_decay=1e-2)
+    o_g = torch.optim.AdamW(mod.parameters(), lr=5e-2, weight_decay=1e-2, fused=True)
+    x = torch.randn(32, 128)
+    for _ in range(3):
+        o_r.zero_grad(); o_g.zero_grad()
+        ref(x).square().mean().backward()
+        mod(x.to(DEV)).square().mean().backward()
+        o_r.step(); o_g.step()
+    with torch.no_grad():
+        assert torch.allclose(mod(x.to(DEV)).cpu(), ref(x), rtol=1e-2, atol=2e-3)
+        assert torch.allclose(mod.weight.cpu(), ref.weight, rtol=1e-3, atol=1e-4)
