@@ -451,27 +451,45 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
         if constexpr (EPI == EPI_LINEAR) {
           const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + c) : 0.f;
           if (col_ok) {
+            if (p.dot_ref != nullptr) {
+              // all 32 reference loads of this chunk are issued before the first is consumed
+              float ref[32];
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr)
+                ref[rr] = (rr < rows_here) ? __ldg(p.dot_ref + (r_base + rr) * p.dot_ref_pitch + c) : 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                if (rr < rows_here) {
+                  const float v = stg[rr * 33 + lane];
+                  partial += v * ref[rr];
+                  p.out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
+                }
+              }
+            } else {
 #pragma unroll 8
-            for (int rr = 0; rr < rows_here; ++rr) {
-              const int64_t r = r_base + rr;
-              float v = stg[rr * 33 + lane];
-              if (p.dot_ref != nullptr) partial += v * __ldg(p.dot_ref + r * p.dot_ref_pitch + c);
-              p.out[r * p.out_pitch + c] = v * scale + bias;
+              for (int rr = 0; rr < rows_here; ++rr) {
+                const float v = stg[rr * 33 + lane];
+                p.out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
+              }
             }
           }
         } else {
           if (col_ok) {
-#pragma unroll 8
-            for (int rr = 0; rr < rows_here; ++rr) {
-              const int64_t r = r_base + rr;
-              const int64_t i = r * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
-              const float g = stg[rr * 33 + lane];
-              const float mk = p.mask ? __ldg(p.mask + i) : 1.f;
-              if (p.tern != nullptr) {
-                const uint32_t code = ((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u;
-                partial += g * ((float)code - 1.f) * (1.f - mk);
+            float mk[32];
+            uint32_t code[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              const int64_t i = (r_base + rr) * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
+              mk[rr] = (p.mask != nullptr && rr < rows_here) ? __ldg(p.mask + i) : 1.f;
+              code[rr] = (p.tern != nullptr && rr < rows_here) ? (((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u) : 1u;
+            }
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              if (rr < rows_here) {
+                const float g = stg[rr * 33 + lane];
+                partial += g * ((float)code[rr] - 1.f) * (1.f - mk[rr]);
+                p.out[(r_base + rr) * p.out_pitch + c] = g * mk[rr];
               }
-              p.out[r * p.out_pitch + c] = g * mk;
             }
           }
         }
