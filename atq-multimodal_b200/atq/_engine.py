@@ -275,7 +275,7 @@ def tgemm_dw_masked(dy_t, x_t, m_out: int, k_in: int, n_tok: int, mask=None, pac
     dw = torch.empty((m_out, k_in), dtype=torch.float32, device=hi.device)
     oa, ob = nv.operand(*dy_t), nv.operand(*x_t)
     dalpha = torch.empty(1, dtype=torch.float32, device=hi.device) if packed is not None else None
-    ws = nv.workspace(nv.lib.atq_workspace_bytes_tgemm(m_out, k_in) if packed is not None else 0, hi.device)
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_tgemm_dw(m_out, k_in, n_tok), hi.device)
     nv.call("atq_tgemm_dw_masked", dev, m_out, k_in, n_tok, ctypes.byref(oa), ctypes.byref(ob), nv.ptr(mask),
             nv.ptr(packed), dw.data_ptr(), k_in, nv.ptr(dalpha), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
     return dw, dalpha

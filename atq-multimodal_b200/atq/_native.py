@@ -68,6 +68,7 @@ _SIGS = {
                               _P, c_int64, _P, c_size_t, _P]),
     "atq_tgemm_dx": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P,
                              c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
+    "atq_workspace_bytes_tgemm_dw": (c_size_t, [c_int64, c_int64, c_int64]),
     "atq_tgemm_dw_masked": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P,
                                     _P, _P, c_int64, _P, _P, c_size_t, _P]),
     "atq_workspace_bytes_colsum": (c_size_t, [c_int64, c_int64]),

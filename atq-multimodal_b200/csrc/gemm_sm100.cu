@@ -121,13 +121,24 @@ __device__ __forceinline__ uint64_t make_smem_desc_kmajor_sw128(uint32_t saddr) 
   return d;
 }
 
+// K-major, SWIZZLE_64B (BLOCK_K = 32: rows of 64 B, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_smem_desc_kmajor_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
+
 // shared-memory matrix descriptor: MN-major, SWIZZLE_128B.  The tile is a row of [64 k x 64 mn] blocks
 // (each 64 rows of 128 B, exactly what one TMA box of a row-major [k, mn] tensor delivers): 64-element
 // MN groups are 8192 B apart (leading byte offset), 8-row K groups 1024 B apart (stride byte offset).
-__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes = 8192) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)(8192 >> 4) << 16;  // leading byte offset: next 64 MN elements
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;  // leading byte offset: next 64 MN elements (= BLOCK_K rows of 128 B)
   d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: next 8 K rows
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
@@ -198,14 +209,16 @@ struct GemmParams {
   float* partials;        // [gridDim.x], nullable
   const uint8_t* b_packed;  // B_PACKED kernels: 2-bit codec bytes of T, [cols, kdim/4] row-major
   int64_t b_packed_pitch;   // bytes per row (= kdim / 4)
+  int splits;               // split-K: work item = (tile, k-range); range s writes out + s * split_stride
+  int64_t split_stride;     // elements
 };
 
 constexpr int kStagingBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp [32][33] fp32 transposition buffers
 
-template <int NUM_A, int NUM_B, int BLOCK_N>
+template <int NUM_A, int NUM_B, int BLOCK_N, int BK = BLOCK_K>
 struct GemmCfg {
-  static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kABytes = BLOCK_M * BK * 2;
+  static constexpr int kBBytes = BLOCK_N * BK * 2;
   static constexpr int kStageBytes = NUM_A * kABytes + NUM_B * kBBytes;
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -219,15 +232,18 @@ struct GemmCfg {
 // (column tile fastest, so the CTAs working at the same time share A tiles through L2 and the
 // whole B operand stays L2-resident).  The accumulator is double-buffered in TMEM: the MMA warp
 // starts tile i+1 while the epilogue warps drain tile i.
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK>
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK, int BK = BLOCK_K>
 __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     tgemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const GemmParams p) {
-  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
+  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N, BK>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool A_MN = (LAYOUT == LAYOUT_MM), B_MN = (LAYOUT != LAYOUT_KK);
   static_assert(!(B_PACKED && LAYOUT != LAYOUT_KK), "packed B is K-major");
+  static_assert(BK == 64 || BK == 32, "BLOCK_K is 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)");
+  static_assert(!(B_PACKED && BK != 64), "the converter writes 128-byte rows");
+  constexpr int kMnBlock = BK * 128;  // bytes of one [BK k x 64 mn] MN-major block
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -244,10 +260,15 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
 
   const int warp_idx = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int num_kb = (int)((p.kdim + BLOCK_K - 1) / BLOCK_K);
+  const int num_kb = (int)((p.kdim + BK - 1) / BK);
   const int tiles_n = (int)((p.cols + BLOCK_N - 1) / BLOCK_N);
   const int tiles_m = (int)((p.rows + BLOCK_M - 1) / BLOCK_M);
   const int num_tiles = tiles_n * tiles_m;
+  const int splits = p.splits > 1 ? p.splits : 1;
+  const int num_work = num_tiles * splits;
+  // work item w -> tile w % num_tiles, k-blocks [kb_lo(w), kb_hi(w)) (balanced, never empty: splits <= num_kb)
+  auto kb_lo = [&](int w) { return (int)(((long long)(w / num_tiles) * num_kb) / splits); };
+  auto kb_hi = [&](int w) { return (int)(((long long)(w / num_tiles + 1) * num_kb) / splits); };
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a_hi);
@@ -277,22 +298,23 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int t = w % num_tiles;
         const int32_t n0 = (t % tiles_n) * BLOCK_N;
         const int32_t m0 = (t / tiles_n) * BLOCK_M;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo(w); kb < kb_hi(w); ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           mbar_expect_tx(full_bar(stage), B_PACKED ? NUM_A * Cfg::kABytes : Cfg::kStageBytes);
-          const int32_t kc = kb * BLOCK_K;
+          const int32_t kc = kb * BK;
           if constexpr (!A_MN) {
             tma_load_2d(sa, &map_a_hi, kc, m0, full_bar(stage));
             if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes, &map_a_lo, kc, m0, full_bar(stage));
           } else {  // [64 k x 64 mn] boxes of the row-major [k, rows] tensor
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j) {
-              tma_load_2d(sa + j * 8192, &map_a_hi, m0 + 64 * j, kc, full_bar(stage));
-              if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes + j * 8192, &map_a_lo, m0 + 64 * j, kc, full_bar(stage));
+              tma_load_2d(sa + j * kMnBlock, &map_a_hi, m0 + 64 * j, kc, full_bar(stage));
+              if (NUM_A == 2) tma_load_2d(sa + Cfg::kABytes + j * kMnBlock, &map_a_lo, m0 + 64 * j, kc, full_bar(stage));
             }
           }
           if constexpr (!B_PACKED) {
@@ -303,8 +325,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
             } else {
 #pragma unroll
               for (int j = 0; j < (BLOCK_N + 63) / 64; ++j) {
-                tma_load_2d(sb + j * 8192, &map_b_hi, n0 + 64 * j, kc, full_bar(stage));
-                if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes + j * 8192, &map_b_lo, n0 + 64 * j, kc, full_bar(stage));
+                tma_load_2d(sb + j * kMnBlock, &map_b_hi, n0 + 64 * j, kc, full_bar(stage));
+                if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes + j * kMnBlock, &map_b_lo, n0 + 64 * j, kc, full_bar(stage));
               }
             }
           }
@@ -319,24 +341,25 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int a = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tmem_empty_bar(a), aphase ^ 1u);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N);
         uint32_t accumulate = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb_lo(w); kb < kb_hi(w); ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
           const uint32_t sb = sa + NUM_A * Cfg::kABytes;
-          const uint64_t da_hi = A_MN ? make_smem_desc_mnmajor_sw128(sa) : make_smem_desc_kmajor_sw128(sa);
-          const uint64_t da_lo = A_MN ? make_smem_desc_mnmajor_sw128(sa + Cfg::kABytes) : make_smem_desc_kmajor_sw128(sa + Cfg::kABytes);
-          const uint64_t db_hi = B_MN ? make_smem_desc_mnmajor_sw128(sb) : make_smem_desc_kmajor_sw128(sb);
-          const uint64_t db_lo = B_MN ? make_smem_desc_mnmajor_sw128(sb + Cfg::kBBytes) : make_smem_desc_kmajor_sw128(sb + Cfg::kBBytes);
+          auto kdesc = [](uint32_t addr) { return BK == 64 ? make_smem_desc_kmajor_sw128(addr) : make_smem_desc_kmajor_sw64(addr); };
+          const uint64_t da_hi = A_MN ? make_smem_desc_mnmajor_sw128(sa, kMnBlock) : kdesc(sa);
+          const uint64_t da_lo = A_MN ? make_smem_desc_mnmajor_sw128(sa + Cfg::kABytes, kMnBlock) : kdesc(sa + Cfg::kABytes);
+          const uint64_t db_hi = B_MN ? make_smem_desc_mnmajor_sw128(sb, kMnBlock) : kdesc(sb);
+          const uint64_t db_lo = B_MN ? make_smem_desc_mnmajor_sw128(sb + Cfg::kBBytes, kMnBlock) : kdesc(sb + Cfg::kBBytes);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          for (int k = 0; k < BK / UMMA_K; ++k) {
             // one K step (16 elements): 32 B inside the swizzled row when K-major, 16 rows of 128 B
             // when MN-major; in 16-byte units
             const uint64_t koa = (uint64_t)(A_MN ? (k * UMMA_K * 128) >> 4 : (k * UMMA_K * 2) >> 4);
@@ -362,7 +385,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     const int ct = threadIdx.x - 6 * 32;  // 0..BLOCK_N-1
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {  // packed kernels are never split (splits == 1)
+      const int t = w % num_tiles;
       const int64_t n0 = (int64_t)(t % tiles_n) * BLOCK_N;
       uint4 cur[kRows];
       auto load_row = [&](int i, int kb) -> uint4 {
@@ -415,11 +439,13 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     const float scale = (EPI == EPI_LINEAR && p.scale != nullptr) ? __ldg(p.scale) : 1.f;
     float partial = 0.f;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int a = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int t = w % num_tiles;
       const int64_t n0 = (int64_t)(t % tiles_n) * BLOCK_N;
       const int64_t m0 = (int64_t)(t / tiles_n) * BLOCK_M;
+      float* const out = p.out + (int64_t)(w / num_tiles) * p.split_stride;  // split-K partial slab
       mbar_wait(tmem_full_bar(a), aphase);
       tcgen05_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
@@ -462,14 +488,14 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
                 if (rr < rows_here) {
                   const float v = stg[rr * 33 + lane];
                   partial += v * ref[rr];
-                  p.out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
+                  out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
                 }
               }
             } else {
 #pragma unroll 8
               for (int rr = 0; rr < rows_here; ++rr) {
                 const float v = stg[rr * 33 + lane];
-                p.out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
+                out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
               }
             }
           }
@@ -488,7 +514,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
               if (rr < rows_here) {
                 const float g = stg[rr * 33 + lane];
                 partial += g * ((float)code[rr] - 1.f) * (1.f - mk[rr]);
-                p.out[(r_base + rr) * p.out_pitch + c] = g * mk[rr];
+                out[(r_base + rr) * p.out_pitch + c] = g * mk[rr];
               }
             }
           }
@@ -526,6 +552,38 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   if (threadIdx.x == 0) *out = (float)s[0];
 }
 
+// split-K second stage for the masked dW GEMM: G = sum_s partial[s] (fixed order), dW = G .* mask,
+// per-CTA partial of sum(G .* T .* (1-mask)) for d(alpha).  Coalesced, one element per thread step.
+__global__ void __launch_bounds__(256)
+    splitk_finalize_masked_kernel(const float* __restrict__ slabs, int splits, int64_t slab_stride, int64_t rows, int64_t cols,
+                                  const float* __restrict__ mask, const uint8_t* __restrict__ tern, float* __restrict__ out,
+                                  int64_t out_pitch, float* __restrict__ partials) {
+  __shared__ float s_part[8];
+  const int64_t n = rows * cols;
+  float partial = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float g = 0.f;
+    for (int s = 0; s < splits; ++s) g += slabs[s * slab_stride + i];
+    const float mk = mask ? __ldg(mask + i) : 1.f;
+    if (tern != nullptr) {
+      const uint32_t code = ((uint32_t)__ldg(tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u;
+      partial += g * ((float)code - 1.f) * (1.f - mk);
+    }
+    const int64_t r = i / cols, c = i - r * cols;
+    out[r * out_pitch + c] = g * mk;
+  }
+  if (partials != nullptr) {
+    partial = warp_sum(partial);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = partial;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += s_part[i];
+      partials[blockIdx.x] = t;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -546,7 +604,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // bf16 [rows, kdim] row-major with pitch; box = [BLOCK_K, box_rows]; OOB reads return zero
-static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t kdim, int64_t pitch, int box_rows) {
+static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t kdim, int64_t pitch, int box_rows, int bk = BLOCK_K) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -554,10 +612,11 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
   }
   cuuint64_t gdim[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld kdim=%lld pitch=%lld ptr=%p", (int)r, (long long)rows, (long long)kdim,
               (long long)pitch, (const void*)ptr);
@@ -567,7 +626,7 @@ static int make_map(CUtensorMap* map, const uint16_t* ptr, int64_t rows, int64_t
 }
 
 // bf16 [kdim, mn] row-major with pitch (MN-major operand); box = [64 mn, 64 k]
-static int make_map_mn(CUtensorMap* map, const uint16_t* ptr, int64_t mn, int64_t kdim, int64_t pitch) {
+static int make_map_mn(CUtensorMap* map, const uint16_t* ptr, int64_t mn, int64_t kdim, int64_t pitch, int bk = BLOCK_K) {
   PFN_encodeTiled enc = get_encode_fn();
   if (enc == nullptr) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -575,7 +634,7 @@ static int make_map_mn(CUtensorMap* map, const uint16_t* ptr, int64_t mn, int64_
   }
   cuuint64_t gdim[2] = {(cuuint64_t)mn, (cuuint64_t)kdim};
   cuuint64_t gstride[1] = {(cuuint64_t)pitch * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)BLOCK_K};
+  cuuint32_t box[2] = {64u, (cuuint32_t)bk};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -587,17 +646,17 @@ static int make_map_mn(CUtensorMap* map, const uint16_t* ptr, int64_t mn, int64_
   return ATQ_OK;
 }
 
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK>
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK, int BK = BLOCK_K>
 static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
-  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N>;
+  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N, BK>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   constexpr bool A_MN = (LAYOUT == LAYOUT_MM), B_MN = (LAYOUT != LAYOUT_KK);
   auto map_a = [&](CUtensorMap* m, const uint16_t* ptr) {
-    return A_MN ? make_map_mn(m, ptr, p.rows, p.kdim, a->pitch) : make_map(m, ptr, p.rows, p.kdim, a->pitch, BLOCK_M);
+    return A_MN ? make_map_mn(m, ptr, p.rows, p.kdim, a->pitch, BK) : make_map(m, ptr, p.rows, p.kdim, a->pitch, BLOCK_M, BK);
   };
   auto map_b = [&](CUtensorMap* m, const uint16_t* ptr) {
-    return B_MN ? make_map_mn(m, ptr, p.cols, p.kdim, b->pitch) : make_map(m, ptr, p.cols, p.kdim, b->pitch, BLOCK_N);
+    return B_MN ? make_map_mn(m, ptr, p.cols, p.kdim, b->pitch, BK) : make_map(m, ptr, p.cols, p.kdim, b->pitch, BLOCK_N, BK);
   };
   if ((r = map_a(&ma_hi, a->hi)) != ATQ_OK) return r;
   if constexpr (!B_PACKED) {
@@ -609,7 +668,7 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
   mb_lo = mb_hi;
   if (NUM_A == 2 && (r = map_a(&ma_lo, a->lo)) != ATQ_OK) return r;
   if (NUM_B == 2 && (r = map_b(&mb_lo, b->lo)) != ATQ_OK) return r;
-  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED, LAYOUT>;
+  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED, LAYOUT, BK>;
   static bool attr_done_dev[64] = {false};  // per instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -628,7 +687,8 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
     return ATQ_EINVAL;
   }
   const int sms = sm_count(dev);
-  const int grid = (int)(tiles < sms ? tiles : sms);
+  const int64_t work = tiles * (p.splits > 1 ? p.splits : 1);
+  const int grid = (int)(work < sms ? work : sms);
   *grid_used = grid;
   kern<<<grid, gemm_threads(B_PACKED, BLOCK_N), Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
   cudaError_t e = cudaGetLastError();
@@ -653,7 +713,18 @@ static int dispatch_layout(const atq_bf16_operand* a, const atq_bf16_operand* b,
     if (b2) ATQ_GO(1, 2, 64);
     ATQ_GO(1, 1, 64);
   }
-  if (a2 && b2) ATQ_GO(2, 2, 128);
+  if (a2 && b2) {
+    // three MMA terms: at BLOCK_N = 128 every tcgen05.mma reads 8 KB of shared memory per 64 cycles (the
+    // 128 B/cycle limit, 82 % tensor-pipe activity measured); 256-wide tiles need 12 KB per 128 cycles.
+    // BLOCK_K = 32 (SWIZZLE_64B rows) keeps four 48 KB stages in shared memory.
+    // ... but only when the wide tiles still fill the machine (small-output / long-K GEMMs such as dW
+    // prefer more, narrower tiles)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int64_t tiles256 = ((p.cols + 255) / 256) * ((p.rows + BLOCK_M - 1) / BLOCK_M) * (p.splits > 1 ? p.splits : 1);
+    if (mid || tiles256 < sm_count(dev)) ATQ_GO(2, 2, 128);
+    return launch_cfg<2, 2, 256, EPI, false, LAYOUT, 32>(a, b, p, stream, grid_used);
+  }
   if (b2) ATQ_GO(1, 2, 128);
   if (mid) {
     if (a2) ATQ_GO(2, 1, 128);
@@ -788,6 +859,26 @@ int atq_tgemm_dx(int device, int64_t n_tokens, int64_t in_features, int64_t out_
                    dalpha_out, ws, ws_bytes, stream);
 }
 
+// split-K plan for the dW GEMM: few output tiles, very long contraction (tokens)
+static int dw_splits(int device, int64_t out_features, int64_t in_features, int64_t n_tokens) {
+  const int64_t tiles = ((in_features + 127) / 128) * ((out_features + BLOCK_M - 1) / BLOCK_M);
+  const int64_t num_kb = (n_tokens + BLOCK_K - 1) / BLOCK_K;
+  const int sms = sm_count(device);
+  if (tiles * 2 > sms || num_kb < 32) return 1;
+  int64_t s = sms / tiles;
+  if (s > 8) s = 8;
+  if (s > num_kb / 8) s = num_kb / 8;
+  return (int)(s < 1 ? 1 : s);
+}
+
+size_t atq_workspace_bytes_tgemm_dw(int64_t out_features, int64_t in_features, int64_t n_tokens) {
+  // CTA partials (d(alpha)) + up to 8 split-K slabs of the [out, in] gradient
+  const int64_t tiles = ((in_features + 127) / 128) * ((out_features + BLOCK_M - 1) / BLOCK_M);
+  const int64_t num_kb = (n_tokens + BLOCK_K - 1) / BLOCK_K;
+  size_t slabs = (tiles * 2 > 256 || num_kb < 32) ? 0 : (size_t)8 * (size_t)out_features * (size_t)in_features * sizeof(float);
+  return atq_workspace_bytes_tgemm(out_features, in_features) + 4096 + ((slabs + 255) & ~(size_t)255);
+}
+
 int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, int64_t n_tokens,
                         const atq_bf16_operand* dy_t, const atq_bf16_operand* x_t, const float* mask,
                         const uint8_t* packed_t, float* dw, int64_t dw_pitch, float* dalpha_out, void* ws,
@@ -800,20 +891,42 @@ int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, i
   ATQ_CHECK_ARG(dy_t->pitch >= (dy_t->mn_major ? out_features : n_tokens) && x_t->pitch >= (x_t->mn_major ? in_features : n_tokens),
                 "operand pitch smaller than its contiguous extent");
   ATQ_CHECK_ARG((packed_t == nullptr) == (dalpha_out == nullptr), "packed_t and dalpha_out go together");
-  if (dalpha_out != nullptr && (ws == nullptr || ws_bytes < atq_workspace_bytes_tgemm(out_features, in_features))) {
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const size_t part_bytes = atq_workspace_bytes_tgemm(out_features, in_features) + 4096;
+  int splits = dw_splits(device, out_features, in_features, n_tokens);
+  const size_t slab_bytes = (size_t)out_features * (size_t)in_features * sizeof(float);
+  if (splits > 1 && (ws == nullptr || ws_bytes < part_bytes + (size_t)splits * slab_bytes)) splits = 1;  // caller sized for no split
+  if (dalpha_out != nullptr && (ws == nullptr || ws_bytes < part_bytes)) {
     set_error("atq_tgemm_dw_masked: workspace too small");
     return ATQ_EWORKSPACE;
   }
-  ATQ_ENSURE_DEVICE(device);
-  cudaStream_t stream = (cudaStream_t)stream_;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.rows = out_features; p.cols = in_features; p.kdim = n_tokens;
-  p.out = dw; p.out_pitch = dw_pitch;
-  p.mask = mask; p.tern = packed_t;
-  p.partials = dalpha_out ? (float*)ws : nullptr;
   int grid = 0;
-  if ((r = dispatch<EPI_MASKED>(dy_t, x_t, p, stream, &grid)) != ATQ_OK) return r;
+  if (splits <= 1) {
+    p.out = dw; p.out_pitch = dw_pitch;
+    p.mask = mask; p.tern = packed_t;
+    p.partials = dalpha_out ? (float*)ws : nullptr;
+    if ((r = dispatch<EPI_MASKED>(dy_t, x_t, p, stream, &grid)) != ATQ_OK) return r;
+  } else {
+    // split-K: every (tile, token-range) work item writes its raw partial product to its slab; the
+    // finalize kernel adds the slabs in fixed order and applies the mask / d(alpha) epilogue
+    float* slabs = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + part_bytes);
+    p.out = slabs; p.out_pitch = in_features;
+    p.splits = splits; p.split_stride = out_features * in_features;
+    if ((r = dispatch<EPI_LINEAR>(dy_t, x_t, p, stream, &grid)) != ATQ_OK) return r;
+    const int64_t n = out_features * in_features;
+    int64_t fg = (n + 256 * 8 - 1) / (256 * 8);
+    const int64_t cap = (int64_t)sm_count(device) * 4;
+    if (fg > cap) fg = cap;
+    if (fg < 1) fg = 1;
+    grid = (int)fg;
+    splitk_finalize_masked_kernel<<<grid, 256, 0, stream>>>(slabs, splits, p.split_stride, out_features, in_features, mask, packed_t,
+                                                             dw, dw_pitch, dalpha_out ? (float*)ws : nullptr);
+    ATQ_LAUNCH_CHECK();
+  }
   if (dalpha_out) {
     reduce_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, grid, dalpha_out);
     ATQ_LAUNCH_CHECK();

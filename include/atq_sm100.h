@@ -191,6 +191,9 @@ int atq_tgemm_dx(int device, int64_t n_tokens, int64_t in_features, int64_t out_
 /* K9 masked dW:  G[M,K] = dY^T[M,N] . X^T[K,N]^T;  dW = G .* mask (mask NULL = STE opt-in: dW = G);
  * dalpha_out (nullable) = sum(G .* T .* (1-mask)), T read from the 2-bit codec bytes
  * (autograd of atq/precision_boost.py:72). */
+/* ws >= atq_workspace_bytes_tgemm_dw(...) enables split-K over the token dimension when the gradient
+ * has few output tiles (deterministic: per-range slabs + fixed-order finalize kernel). */
+size_t atq_workspace_bytes_tgemm_dw(int64_t out_features, int64_t in_features, int64_t n_tokens);
 int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, int64_t n_tokens,
                         const atq_bf16_operand* dy_t, const atq_bf16_operand* x_t,
                         const float* mask, const uint8_t* packed_t,

@@ -286,7 +286,8 @@ def test_ternary_linear_packed_policy(policy):
 
 
 @pytest.mark.parametrize("rows,cols,k", [(128, 128, 64), (300, 200, 136), (16, 1, 96), (800, 192, 192), (192, 384, 800),
-                                         (257, 10, 128), (96, 192, 16), (1000, 520, 1064), (4096, 4096, 1024)])
+                                         (257, 10, 128), (96, 192, 16), (1000, 520, 1064), (4096, 4096, 1024),
+                                         (192, 192, 4096), (768, 768, 8200), (1, 96, 2048)])
 def test_tgemm_mn_major_operands(rows, cols, k):
     """dX reads B as [k, cols] row-major, dW reads A as [k, rows] and B as [k, cols] row-major (MN-major UMMA
     descriptors, no transposes): same result as the K-major path on explicitly transposed copies."""
@@ -333,3 +334,23 @@ def test_fused_optimizer_step_invalidates_cache():
     with torch.no_grad():
         assert torch.allclose(mod(x.to(DEV)).cpu(), ref(x), rtol=1e-2, atol=2e-3)
         assert torch.allclose(mod.weight.cpu(), ref.weight, rtol=1e-3, atol=1e-4)
+
+
+def test_dw_split_k_masked_epilogue_long_contraction():
+    """dW with few output tiles and a long token dimension takes the split-K path (per-range slabs + fixed-order
+    finalize): mask, d(alpha) reduction and determinism."""
+    g = torch.Generator().manual_seed(4)
+    m_out, k_in, n_tok = 192, 384, 6000
+    dy = torch.randn(n_tok, m_out, generator=g)
+    x = torch.randn(n_tok, k_in, generator=g)
+    mask = (torch.rand(m_out, k_in, generator=g) < 0.2).float()
+    tq = torch.randint(-1, 2, (m_out, k_in), generator=g).float()
+    packed, _ = eng.pack2_from_f32(tq.to(DEV).reshape(-1))
+    ga, xa = eng.split_bf16(dy.to(DEV), True), eng.split_bf16(x.to(DEV), True)
+    dw, dalpha = eng.tgemm_dw_masked(ga + (1,), xa + (1,), m_out, k_in, n_tok, mask=mask.to(DEV), packed=packed)
+    G = dy.double().t() @ x.double()
+    assert torch.allclose(dw.cpu().double(), G * mask.double(), **TOL)
+    want = float((G * tq.double() * (1 - mask.double())).sum())
+    assert abs(float(dalpha) - want) <= 1e-3 * abs(want) + 5e-2
+    dw2, dalpha2 = eng.tgemm_dw_masked(ga + (1,), xa + (1,), m_out, k_in, n_tok, mask=mask.to(DEV), packed=packed)
+    assert torch.equal(dw, dw2) and torch.equal(dalpha, dalpha2)  # bitwise reproducible
