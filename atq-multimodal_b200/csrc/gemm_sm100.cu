@@ -213,7 +213,7 @@ struct GemmParams {
   int64_t split_stride;     // elements
 };
 
-constexpr int kStagingBytes = 4 * 32 * 33 * 4;  // per-epilogue-warp [32][33] fp32 transposition buffers
+constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp [32][36] fp32 transposition buffers (rows 16-byte aligned)
 
 template <int NUM_A, int NUM_B, int BLOCK_N, int BK = BLOCK_K>
 struct GemmCfg {
@@ -435,9 +435,17 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     // through a private shared-memory buffer so that every global access below is a warp-wide
     // 128-byte row segment: lane = column.
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes) + (warp_idx - 2) * (32 * 33);
+    float* stg = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes) + (warp_idx - 2) * (32 * 36);
     const float scale = (EPI == EPI_LINEAR && p.scale != nullptr) ? __ldg(p.scale) : 1.f;
     float partial = 0.f;
+    // 128-bit path: every lane owns 4 consecutive columns of 8 rows per chunk (4x fewer shared/global
+    // instructions than lane = column); needs 16-byte aligned rows on every tensor the epilogue touches
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
+    const bool vec_ok = ((p.cols | p.out_pitch | p.split_stride) & 3) == 0 && al16(p.out) &&
+                        (EPI == EPI_LINEAR ? ((p.bias == nullptr || al16(p.bias)) &&
+                                              (p.dot_ref == nullptr || (al16(p.dot_ref) && (p.dot_ref_pitch & 3) == 0)))
+                                           : (p.mask == nullptr || al16(p.mask)));
+    const int vq = lane & 7, vrg = lane >> 3;
     int it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
       const int a = it & 1;
@@ -446,80 +454,137 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       const int64_t n0 = (int64_t)(t % tiles_n) * BLOCK_N;
       const int64_t m0 = (int64_t)(t / tiles_n) * BLOCK_M;
       float* const out = p.out + (int64_t)(w / num_tiles) * p.split_stride;  // split-K partial slab
-      mbar_wait(tmem_full_bar(a), aphase);
-      tcgen05_fence_after();
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
       const int64_t r_base = m0 + quarter * 32;
       // number of 32-column chunks of this tile that hold real output (warp-uniform)
       int nch = (int)((p.cols - n0 + 31) / 32);
       if (nch > BLOCK_N / 32) nch = BLOCK_N / 32;
       if (r_base >= p.rows) nch = 0;
+      const int rows_here = (int)((p.rows - r_base) < 32 ? (p.rows - r_base) : 32);
+      // Side inputs of the epilogue (mask + codec bytes, or the dot-product reference) do not depend on the
+      // accumulator: chunk 0 is fetched BEFORE waiting for the MMAs and chunk ch+1 while chunk ch is
+      // processed, so short GEMMs do not pay one memory latency per chunk after the mainloop.
+      const bool side = (EPI == EPI_MASKED) || p.dot_ref != nullptr;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
+      if (vec_ok) {
+        // ---- 128-bit path ----
+        auto load_side_v = [&](int ch, float4 (&f)[8], uint32_t (&cd)[8]) {
+          const int64_t c = n0 + ch * 32 + 4 * vq;
+          const bool col_ok = c < p.cols;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int row = 4 * g + vrg;
+            const bool ok = col_ok && row < rows_here;
+            if constexpr (EPI == EPI_LINEAR) {
+              f[g] = ok ? __ldg(reinterpret_cast<const float4*>(p.dot_ref + (r_base + row) * p.dot_ref_pitch + c))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              const int64_t i = (r_base + row) * p.cols + c;  // multiple of 4: one codec byte per group
+              f[g] = (p.mask != nullptr && ok) ? __ldg(reinterpret_cast<const float4*>(p.mask + i)) : make_float4(1.f, 1.f, 1.f, 1.f);
+              cd[g] = (p.tern != nullptr && ok) ? (uint32_t)__ldg(p.tern + (i >> 2)) : 0x55u;
+            }
+          }
+        };
+        float4 vf[8];
+        uint32_t vc[8];
+        if (side && nch > 0) load_side_v(0, vf, vc);
+        mbar_wait(tmem_full_bar(a), aphase);
+        tcgen05_fence_after();
+        if (nch == 0) {
+          tcgen05_fence_before();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < nch; ++ch) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(ch * 32), acc);
+          float4 nf[8];
+          uint32_t nc[8];
+          if (side && ch + 1 < nch) load_side_v(ch + 1, nf, nc);
+          tmem_ld_wait();
+          if (ch == nch - 1) {  // everything this warp needs has left TMEM: hand the buffer back
+            tcgen05_fence_before();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+          }
+          // thread = accumulator row: 8 x 16-byte stores, 144-byte row pitch (conflict-free per quarter-warp)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 36 + 4 * j) = make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          __syncwarp();
+          const int64_t c = n0 + ch * 32 + 4 * vq;
+          const bool col_ok = c < p.cols;
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (EPI == EPI_LINEAR) {
+            if (p.bias != nullptr && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int row = 4 * g + vrg;
+            if (col_ok && row < rows_here) {
+              const float4 v = *reinterpret_cast<const float4*>(stg + row * 36 + 4 * vq);
+              float4 o;
+              if constexpr (EPI == EPI_LINEAR) {
+                if (p.dot_ref != nullptr) partial += (v.x * vf[g].x + v.y * vf[g].y) + (v.z * vf[g].z + v.w * vf[g].w);
+                o = make_float4(v.x * scale + bias4.x, v.y * scale + bias4.y, v.z * scale + bias4.z, v.w * scale + bias4.w);
+              } else {
+                const uint32_t b = vc[g];
+                const float t0 = (float)(b & 3u) - 1.f, t1 = (float)((b >> 2) & 3u) - 1.f;
+                const float t2 = (float)((b >> 4) & 3u) - 1.f, t3 = (float)((b >> 6) & 3u) - 1.f;
+                const float4 mk = vf[g];
+                partial += (v.x * t0 * (1.f - mk.x) + v.y * t1 * (1.f - mk.y)) + (v.z * t2 * (1.f - mk.z) + v.w * t3 * (1.f - mk.w));
+                o = make_float4(v.x * mk.x, v.y * mk.y, v.z * mk.z, v.w * mk.w);
+              }
+              *reinterpret_cast<float4*>(out + (r_base + row) * p.out_pitch + c) = o;
+            }
+          }
+          if (side && ch + 1 < nch) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              vf[g] = nf[g];
+              if constexpr (EPI == EPI_MASKED) vc[g] = nc[g];
+            }
+          }
+          __syncwarp();  // staging buffer reuse + reconverge before the next warp-aligned tcgen05.ld
+        }
+        continue;
+      }
+      // ---- scalar path (columns / pitches that are not multiples of 4, unaligned views): lane = column ----
+      mbar_wait(tmem_full_bar(a), aphase);
+      tcgen05_fence_after();
       if (nch == 0) {
         tcgen05_fence_before();
         if (lane == 0) mbar_arrive(tmem_empty_bar(a));
       }
 #pragma unroll 1
       for (int ch = 0; ch < nch; ++ch) {
-        const int64_t c0 = n0 + ch * 32;
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(ch * 32), acc);
         tmem_ld_wait();
-        if (ch == nch - 1) {  // everything this warp needs has left TMEM: hand the buffer back
+        if (ch == nch - 1) {
           tcgen05_fence_before();
           if (lane == 0) mbar_arrive(tmem_empty_bar(a));
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(acc[j]);  // bank (lane+j)%32: conflict-free
+        for (int j = 0; j < 32; ++j) stg[lane * 36 + j] = __uint_as_float(acc[j]);  // 4-way bank conflict accepted here
         __syncwarp();
-        const int64_t c = c0 + lane;
-        const bool col_ok = c < p.cols;
-        const int rows_here = (int)((p.rows - r_base) < 32 ? (p.rows - r_base) : 32);
-        if constexpr (EPI == EPI_LINEAR) {
-          const float bias = (p.bias != nullptr && col_ok) ? __ldg(p.bias + c) : 0.f;
-          if (col_ok) {
-            if (p.dot_ref != nullptr) {
-              // all 32 reference loads of this chunk are issued before the first is consumed
-              float ref[32];
-#pragma unroll
-              for (int rr = 0; rr < 32; ++rr)
-                ref[rr] = (rr < rows_here) ? __ldg(p.dot_ref + (r_base + rr) * p.dot_ref_pitch + c) : 0.f;
-#pragma unroll
-              for (int rr = 0; rr < 32; ++rr) {
-                if (rr < rows_here) {
-                  const float v = stg[rr * 33 + lane];
-                  partial += v * ref[rr];
-                  out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
-                }
-              }
+        const int64_t c = n0 + ch * 32 + lane;
+        if (c < p.cols) {
+          const float bias = (EPI == EPI_LINEAR && p.bias != nullptr) ? __ldg(p.bias + c) : 0.f;
+#pragma unroll 4
+          for (int rr = 0; rr < rows_here; ++rr) {
+            const float v = stg[rr * 36 + lane];
+            if constexpr (EPI == EPI_LINEAR) {
+              if (p.dot_ref != nullptr) partial += v * __ldg(p.dot_ref + (r_base + rr) * p.dot_ref_pitch + c);
+              out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
             } else {
-#pragma unroll 8
-              for (int rr = 0; rr < rows_here; ++rr) {
-                const float v = stg[rr * 33 + lane];
-                out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
-              }
-            }
-          }
-        } else {
-          if (col_ok) {
-            float mk[32];
-            uint32_t code[32];
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
               const int64_t i = (r_base + rr) * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
-              mk[rr] = (p.mask != nullptr && rr < rows_here) ? __ldg(p.mask + i) : 1.f;
-              code[rr] = (p.tern != nullptr && rr < rows_here) ? (((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u) : 1u;
-            }
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-              if (rr < rows_here) {
-                const float g = stg[rr * 33 + lane];
-                partial += g * ((float)code[rr] - 1.f) * (1.f - mk[rr]);
-                out[(r_base + rr) * p.out_pitch + c] = g * mk[rr];
-              }
+              const float mk = p.mask != nullptr ? __ldg(p.mask + i) : 1.f;
+              const uint32_t code = p.tern != nullptr ? (((uint32_t)__ldg(p.tern + (i >> 2)) >> (2 * (int)(i & 3))) & 3u) : 1u;
+              partial += v * ((float)code - 1.f) * (1.f - mk);
+              out[(r_base + rr) * p.out_pitch + c] = v * mk;
             }
           }
         }
-        __syncwarp();  // staging buffer reuse + reconverge before the next warp-aligned tcgen05.ld
+        __syncwarp();
       }
     }
     if (p.partials != nullptr) {

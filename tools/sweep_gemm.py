@@ -14,7 +14,7 @@ import atq._engine as eng
 dev = torch.device("cuda:0")
 peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"bf16_tflops": 1590.0}
 flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-sizes = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [4096]
+sizes = [tuple(int(b) for b in a.split("x")) if "x" in a else (int(a), int(a)) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [(4096, 4096)]  # OUTxIN
 tokens = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1024, 8192, 65536]
 reps = 5
 
@@ -32,16 +32,17 @@ def timeit(fn):
     return tot / reps
 
 
-for MK in sizes:
-    for kind in ("ternary", "rpb0.05", "rpb0.2"):
+kinds = sys.argv[3].split(",") if len(sys.argv) > 3 else ["ternary", "rpb0.05", "rpb0.2"]
+for OUT, IN in sizes:
+    for kind in kinds:
         torch.manual_seed(0)
         if kind == "ternary":
-            mod = atq.TernaryLinear(MK, MK).to(dev)
+            mod = atq.TernaryLinear(IN, OUT).to(dev)
         else:
-            mod = atq.ResidualPrecisionBoostLinear(MK, MK, float(kind[3:]), True, 0.3).to(dev)
+            mod = atq.ResidualPrecisionBoostLinear(IN, OUT, float(kind[3:]), True, 0.3).to(dev)
         for N in tokens:
-            x = torch.randn(N, MK, device=dev)
-            gy = torch.randn(N, MK, device=dev)
+            x = torch.randn(N, IN, device=dev)
+            gy = torch.randn(N, OUT, device=dev)
             for mode in ("parity", "fast"):
                 atq.set_gemm_mode(mode)
                 mod._ops.key = None
@@ -62,8 +63,8 @@ for MK in sizes:
                 ms_f = timeit(lambda: torch.no_grad()(lambda: mod(x))())
                 ms_fb = timeit(fwdbwd)
                 n_gemm = 2 if kind == "ternary" else 3
-                flops_f = 2.0 * N * MK * MK
-                rec = {"M": MK, "K": MK, "tokens": N, "layer": kind, "mode": mode,
+                flops_f = 2.0 * N * OUT * IN
+                rec = {"M": OUT, "K": IN, "tokens": N, "layer": kind, "mode": mode,
                        "fwd_ms": round(ms_f, 4), "fwd_tflops": round(flops_f / ms_f / 1e9, 1),
                        "fwdbwd_ms": round(ms_fb, 4), "fwdbwd_tflops": round(n_gemm * flops_f / ms_fb / 1e9, 1),
                        "fwdbwd_frac_of_bf16_peak": round(n_gemm * flops_f / ms_fb / 1e9 / peaks["bf16_tflops"], 4),
