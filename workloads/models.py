@@ -25,6 +25,11 @@ def _lengths_to_mask(lengths, batch, seq, device):
     return torch.arange(seq, device=device).expand(batch, seq) >= lengths.to(device).unsqueeze(1)
 
 
+# True: the softmax(QK^T)V core of TernaryAttention runs as one fused SDPA kernel (forward) + one (backward)
+# instead of materialising the score tensors; False: the reference's explicit matmul/softmax/dropout sequence.
+FUSED_ATTENTION_CORE = True
+
+
 class TernaryAttention(nn.Module):
     """models/text_encoder.py:10-163 (TernaryMultiheadAttention, critical_attention=True)."""
 
@@ -62,6 +67,15 @@ class TernaryAttention(nn.Module):
         q = q.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
         k = k.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
         v = v.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
+        if FUSED_ATTENTION_CORE:
+            # same maths as the explicit branch below (softmax(q k^T * scale + key mask) -> dropout -> . v) through
+            # torch's fused scaled-dot-product kernel: no [B, h, L, L] score tensors in HBM, no head transposes.
+            # The attention core is fp32 torch code in the reference (outside the atq package).
+            attn_mask = None if key_padding_mask is None else ~key_padding_mask[:, None, None, :]
+            out = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask, scale=self.attention_scale,
+                                                 dropout_p=self.dropout.p if self.training else 0.0)
+            out = out.transpose(1, 2).reshape(b, -1, self.embed_dim)
+            return self.out_proj(out) + 0.1 * query
         scores = torch.matmul(q, k.transpose(-2, -1)) * self.attention_scale
         if key_padding_mask is not None:
             scores = scores.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
