@@ -1,0 +1,721 @@
+// Fused attention core for the ternary transformer blocks:
+//
+//   O = dropout(softmax(scale * Q K^T + key_padding_mask)) V        per (batch, head), head_dim 64
+//
+// replaces the reference's explicit matmul / masked_fill / softmax / dropout / matmul sequence
+// (models/text_encoder.py:117-163, TernaryMultiheadAttention._scaled_dot_product_attention) and its
+// autograd backward.  Q, K, V are the fp32 outputs of the ternary q/k/v projections, read in place
+// from their [B*L, E] layout (head h = columns 64h..64h+63): no head transposes, no [B,h,L,L] score
+// tensors in HBM.
+//
+// One CTA (128 threads) per (batch, head).  fp32 tiles are converted on the fly to bf16 (hi, lo) pairs
+// and stored with the SWIZZLE_128B pattern UMMA descriptors expect (16-byte chunk c of row r at chunk
+// c ^ (r & 7)); one thread issues tcgen05.mma (S = Q K^T with terms hi*hi, lo*hi, hi*lo; P V with V hi/lo),
+// accumulators live in TMEM, every thread owns one accumulator row (query) for the softmax.
+// The same shared-memory image of a [rows x 64] tile serves as a K-major operand (contraction over the
+// 64 head dims) and as an MN-major operand (contraction over the rows) - only the descriptor differs.
+//
+// Dropout uses a counter-based hash of (seed, batch*head*L + query, key) so that the backward kernel
+// regenerates the mask; the seed is read from device memory (CUDA-graph safe).
+#include "common.cuh"
+#include "tc_sm100.cuh"
+#include "../../include/atq_sm100.h"
+
+namespace atq {
+
+constexpr int kHd = 64;          // head dim
+constexpr int kAttThreads = 128;
+constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
+
+struct AttnParams {
+  const float *q, *k, *v;
+  int64_t q_pitch, k_pitch, v_pitch;
+  const uint8_t* key_pad;  // [B, L], non-zero = padded key; nullable
+  float* out;
+  int64_t out_pitch;
+  float* lse;  // [B*H, L] log-sum-exp of the scaled, masked scores
+  int B, H, L, NK;  // NK = L rounded up to 32 (forward) / key tile 128 (backward)
+  float scale;
+  uint32_t drop_thresh;  // keep iff hash >= thresh; 0 = no dropout
+  float inv_keep;
+  const unsigned long long* seed;  // device scalar, nullable (= 0)
+  int terms;  // 3 = hi/lo split (parity), 1 = bf16 only (fast)
+  // backward
+  const float *o, *dout;
+  int64_t o_pitch, do_pitch;
+  float *dq, *dk, *dv;
+  int64_t dq_pitch, dk_pitch, dv_pitch;
+};
+
+__device__ __forceinline__ uint32_t drop_row_key(uint32_t seed_lo, uint32_t row_id) {
+  uint32_t x = (row_id * 0x9E3779B1u) ^ seed_lo;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_hash(uint32_t row_key, uint32_t seed_hi, uint32_t key) {
+  uint32_t x = row_key + key * 0xC2B2AE35u + seed_hi;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(uint16_t lo_elem, uint16_t hi_elem) { return (uint32_t)lo_elem | ((uint32_t)hi_elem << 16); }
+
+// fp32 [rows_valid x 64] (row pitch in floats, 16-byte aligned rows) -> bf16 hi (+ lo) tiles of rows_total
+// swizzled 128-byte rows; rows >= rows_valid become zeros.  8 threads per row (32 B of fp32 each).
+template <bool LO>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t pitch, int rows_valid, int rows_total,
+                                           uint32_t s_hi, uint32_t s_lo) {
+  const int c = threadIdx.x & 7;
+  constexpr int kRowsPerPass = kAttThreads / 8;  // 16
+  for (int r0 = threadIdx.x >> 3; r0 < rows_total; r0 += 4 * kRowsPerPass) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // all loads of four passes in flight before the first conversion
+      const int r = r0 + i * kRowsPerPass;
+      if (r < rows_valid) {
+        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * pitch + 8 * c);
+        a[i] = __ldg(p);
+        b[i] = __ldg(p + 1);
+      } else {
+        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        b[i] = a[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + i * kRowsPerPass;
+      if (r < rows_total) {
+        const float x[8] = {a[i].x, a[i].y, a[i].z, a[i].w, b[i].x, b[i].y, b[i].z, b[i].w};
+        uint16_t h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_bf16(x[j], h[j], l[j]);
+        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4);
+        st_shared_v4(s_hi + off, make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7])));
+        if (LO) st_shared_v4(s_lo + off, make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7])));
+      }
+    }
+  }
+}
+
+// one accumulator row (this thread's TMEM lane), 32 consecutive columns
+__device__ __forceinline__ void ld_row32(uint32_t taddr, float (&f)[32]) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
+}
+
+// write 32 bf16 values (keys 32*ch .. 32*ch+31 of row `row`) into a K-major [128 x 64k] atom sequence
+__device__ __forceinline__ void store_row32_bf16(uint32_t base, int row, int ch, const float (&v)[32]) {
+  const uint32_t atom = base + (uint32_t)(ch >> 1) * (uint32_t)kTileBytes + (uint32_t)row * 128u;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16_bits(v[8 * g + 2 * j]), bf16_bits(v[8 * g + 2 * j + 1]));
+    const uint32_t chunk = (uint32_t)((ch & 1) * 4 + g);
+    st_shared_v4(atom + ((chunk ^ ((uint32_t)row & 7u)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+  }
+}
+
+// residual of the bf16 rounding: v - bf16(v), rounded to bf16 (second pass of a hi/lo operand that has to go
+// through the same shared-memory buffer)
+__device__ __forceinline__ void store_row32_bf16_residual(uint32_t base, int row, int ch, const float (&v)[32]) {
+  float r[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) r[j] = v[j] - bf16_bits_to_float(bf16_bits(v[j]));
+  store_row32_bf16(base, row, ch, r);
+}
+
+// this thread's accumulator row: write 32 consecutive TMEM columns back (fp32)
+__device__ __forceinline__ void st_row32(uint32_t taddr, const float (&f)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(f[0])), "r"(__float_as_uint(f[1])), "r"(__float_as_uint(f[2])), "r"(__float_as_uint(f[3])),
+      "r"(__float_as_uint(f[4])), "r"(__float_as_uint(f[5])), "r"(__float_as_uint(f[6])), "r"(__float_as_uint(f[7])),
+      "r"(__float_as_uint(f[8])), "r"(__float_as_uint(f[9])), "r"(__float_as_uint(f[10])), "r"(__float_as_uint(f[11])),
+      "r"(__float_as_uint(f[12])), "r"(__float_as_uint(f[13])), "r"(__float_as_uint(f[14])), "r"(__float_as_uint(f[15])),
+      "r"(__float_as_uint(f[16])), "r"(__float_as_uint(f[17])), "r"(__float_as_uint(f[18])), "r"(__float_as_uint(f[19])),
+      "r"(__float_as_uint(f[20])), "r"(__float_as_uint(f[21])), "r"(__float_as_uint(f[22])), "r"(__float_as_uint(f[23])),
+      "r"(__float_as_uint(f[24])), "r"(__float_as_uint(f[25])), "r"(__float_as_uint(f[26])), "r"(__float_as_uint(f[27])),
+      "r"(__float_as_uint(f[28])), "r"(__float_as_uint(f[29])), "r"(__float_as_uint(f[30])), "r"(__float_as_uint(f[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// same, as a (hi, lo) pair: v = hi + lo to ~16 mantissa bits
+__device__ __forceinline__ void store_row32_bf16_hilo(uint32_t base_hi, uint32_t base_lo, int row, int ch, const float (&v)[32]) {
+  const uint32_t off = (uint32_t)(ch >> 1) * (uint32_t)kTileBytes + (uint32_t)row * 128u;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t wh[4], wl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint16_t h0, l0, h1, l1;
+      split_bf16(v[8 * g + 2 * j], h0, l0);
+      split_bf16(v[8 * g + 2 * j + 1], h1, l1);
+      wh[j] = pack_bf16x2(h0, h1);
+      wl[j] = pack_bf16x2(l0, l1);
+    }
+    const uint32_t chunk = ((uint32_t)((ch & 1) * 4 + g) ^ ((uint32_t)row & 7u)) << 4;
+    st_shared_v4(base_hi + off + chunk, make_uint4(wh[0], wh[1], wh[2], wh[3]));
+    st_shared_v4(base_lo + off + chunk, make_uint4(wl[0], wl[1], wl[2], wl[3]));
+  }
+}
+
+// key validity bits (key < L and not padded) for up to 256 keys -> s_valid[8]
+__device__ __forceinline__ void build_valid_bits(const AttnParams& p, int b, uint32_t* s_valid) {
+  for (int k0 = 0; k0 < 256; k0 += kAttThreads) {
+    const int k = k0 + (int)threadIdx.x;
+    bool ok = k < p.L;
+    if (ok && p.key_pad != nullptr) ok = p.key_pad[(int64_t)b * p.L + k] == 0;
+    const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) s_valid[k >> 5] = bits;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+// shared memory: [K hi | K lo | V hi | V lo] (NK rows x 128 B each), [Q hi | Q lo] (128 rows), P (NK/64 atoms)
+__global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int NK = p.NK;
+  const bool lo = p.terms == 3;
+  const uint32_t kv_bytes = (uint32_t)NK * 128u;
+  const uint32_t s_kh = base, s_kl = s_kh + kv_bytes;
+  const uint32_t s_vh = s_kl + (lo ? kv_bytes : 0u), s_vl = s_vh + kv_bytes;
+  const uint32_t s_qh = s_vl + (lo ? kv_bytes : 0u), s_ql = s_qh + kTileBytes;
+  const uint32_t s_p = s_ql + (lo ? (uint32_t)kTileBytes : 0u);
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_valid[8];
+  const uint32_t bar = smem_u32(&s_bar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
+  const int L = p.L;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&s_tmem));
+  build_valid_bits(p, b, s_valid);
+  const float* kg = p.k + (int64_t)b * L * p.k_pitch + h * kHd;
+  const float* vg = p.v + (int64_t)b * L * p.v_pitch + h * kHd;
+  if (lo) {
+    stage_tile<true>(kg, p.k_pitch, L, NK, s_kh, s_kl);
+    stage_tile<true>(vg, p.v_pitch, L, NK, s_vh, s_vl);
+  } else {
+    stage_tile<false>(kg, p.k_pitch, L, NK, s_kh, 0);
+    stage_tile<false>(vg, p.v_pitch, L, NK, s_vh, 0);
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+  const uint32_t t_s = tmem, t_o = tmem + 256u;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const unsigned long long seed = p.seed != nullptr ? *p.seed : 0ull;
+  const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
+  const float c2 = p.scale * 1.4426950408889634f;
+  uint32_t phase = 0;
+
+  for (int q0 = 0; q0 < L; q0 += 128) {
+    const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
+    const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * kHd;
+    if (lo) stage_tile<true>(qg, p.q_pitch, q_valid, 128, s_qh, s_ql);
+    else stage_tile<false>(qg, p.q_pitch, q_valid, 128, s_qh, 0);
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tcgen05_fence_after();
+      const uint32_t idesc = make_idesc_rt(NK, false, false);
+      uint32_t acc = 0;
+      for (int term = 0; term < p.terms; ++term) {
+        const uint32_t sa = term == 1 ? s_ql : s_qh, sb = term == 2 ? s_kl : s_kh;
+        const uint64_t da = make_smem_desc_kmajor_sw128(sa), db = make_smem_desc_kmajor_sw128(sb);
+#pragma unroll
+        for (int j = 0; j < kHd / UMMA_K; ++j) {
+          umma_bf16(t_s, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tcgen05_fence_after();
+
+    // ---- softmax: this thread owns query q0 + threadIdx.x ----
+    const int row = threadIdx.x;
+    const uint32_t t_row = t_s + lane_off;
+    float m = -INFINITY;
+    for (int ch = 0; ch < NK / 32; ++ch) {
+      float s[32];
+      ld_row32(t_row + (uint32_t)(ch * 32), s);
+      const uint32_t vb = s_valid[ch];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if ((vb >> j) & 1u) m = fmaxf(m, s[j]);
+    }
+    if (m == -INFINITY) m = 0.f;  // every key masked: probabilities are all zero below
+    const uint32_t row_key = drop_row_key(seed_lo, (uint32_t)(bh * L + q0 + row));
+    float sum = 0.f;
+    for (int ch = 0; ch < NK / 32; ++ch) {
+      float s[32];
+      ld_row32(t_row + (uint32_t)(ch * 32), s);
+      const uint32_t vb = s_valid[ch];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float pj = ((vb >> j) & 1u) ? exp2f((s[j] - m) * c2) : 0.f;
+        sum += pj;
+        if (p.drop_thresh != 0u) pj = drop_hash(row_key, seed_hi, (uint32_t)(ch * 32 + j)) >= p.drop_thresh ? pj * p.inv_keep : 0.f;
+        s[j] = pj;
+      }
+      store_row32_bf16(s_p, row, ch, s);
+      if (lo) st_row32(t_row + (uint32_t)(ch * 32), s);  // keep the fp32 probabilities for the lo pass
+    }
+    if (lo) tmem_st_wait();
+    fence_proxy_async();
+    tcgen05_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tcgen05_fence_after();
+      const uint32_t idesc = make_idesc_rt(kHd, false, true);
+      uint32_t acc = 0;
+      const int vterms = lo ? 2 : 1;
+      for (int term = 0; term < vterms; ++term) {  // P_hi V_hi, P_hi V_lo
+        const uint32_t sb = term == 1 ? s_vl : s_vh;
+        for (int j = 0; j < NK / UMMA_K; ++j) {
+          const uint64_t da = make_smem_desc_kmajor_sw128(s_p + (uint32_t)(j >> 2) * (uint32_t)kTileBytes + (uint32_t)(j & 3) * 32u);
+          const uint64_t db = make_smem_desc_mnmajor_sw128(sb + (uint32_t)j * 2048u, 8192);
+          umma_bf16(t_o, da, db, idesc, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+    tcgen05_fence_after();
+    if (lo) {
+      // second pass through the same P buffer: P_lo = p - bf16(p) (a single bf16 P leaves ~3e-3 absolute error)
+      for (int ch = 0; ch < NK / 32; ++ch) {
+        float s[32];
+        ld_row32(t_row + (uint32_t)(ch * 32), s);
+        store_row32_bf16_residual(s_p, row, ch, s);
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_rt(kHd, false, true);
+        for (int j = 0; j < NK / UMMA_K; ++j) {  // + P_lo V_hi
+          const uint64_t da = make_smem_desc_kmajor_sw128(s_p + (uint32_t)(j >> 2) * (uint32_t)kTileBytes + (uint32_t)(j & 3) * 32u);
+          const uint64_t db = make_smem_desc_mnmajor_sw128(s_vh + (uint32_t)j * 2048u, 8192);
+          umma_bf16(t_o, da, db, idesc, 1u);
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tcgen05_fence_after();
+    }
+
+    // ---- epilogue: normalise and store this query's 64 outputs ----
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    const int q = q0 + row;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float o[32];
+      ld_row32(t_o + lane_off + (uint32_t)(half * 32), o);
+      if (q < L) {
+        float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)b * L + q) * p.out_pitch + h * kHd + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+      }
+    }
+    if (q < L && p.lse != nullptr) p.lse[(int64_t)bh * L + q] = sum > 0.f ? m * p.scale + logf(sum) : -INFINITY;
+    tcgen05_fence_before();
+    __syncthreads();  // TMEM and the Q / P tiles are reused by the next query tile
+    tcgen05_fence_after();
+  }
+  if (warp == 0) tmem_dealloc<512>(tmem);
+  (void)lane;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+// shared memory (1024-aligned 16 KB tiles): K hi, K lo, V hi, V lo, Q hi, Q lo, dO hi, dO lo, then P, dS hi and
+// dS lo (two 64-key atoms each; dS carries a lo part because dQ / dK are sums of dS-weighted rows and a single
+// bf16 dS leaves ~3e-3 absolute error, above the 1e-3 tolerance).  TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448).
+__global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const bool lo = p.terms == 3;
+  const uint32_t T = (uint32_t)kTileBytes;
+  const uint32_t s_kh = base, s_kl = base + T, s_vh = base + 2 * T, s_vl = base + 3 * T;
+  const uint32_t s_qh = base + 4 * T, s_ql = base + 5 * T, s_dh = base + 6 * T, s_dl = base + 7 * T;
+  const uint32_t s_p = base + 8 * T, s_ds = base + 10 * T, s_dsl = base + 12 * T;
+  __shared__ __align__(8) unsigned long long s_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_valid[8];
+  const uint32_t bar = smem_u32(&s_bar);
+  const int warp = threadIdx.x >> 5;
+  const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
+  const int L = p.L;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(smem_u32(&s_tmem));
+  build_valid_bits(p, b, s_valid);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
+  const uint32_t t_s = tmem, t_dp = tmem + 128u, t_dq = tmem + 256u, t_dk = tmem + 320u, t_dv = tmem + 384u;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const unsigned long long seed = p.seed != nullptr ? *p.seed : 0ull;
+  const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
+  const float c2 = p.scale * 1.4426950408889634f;
+  const int row = threadIdx.x;
+  uint32_t phase = 0;
+
+  for (int k0 = 0; k0 < L; k0 += 128) {
+    const int k_valid = (L - k0) < 128 ? (L - k0) : 128;
+    const float* kg = p.k + ((int64_t)b * L + k0) * p.k_pitch + h * kHd;
+    const float* vg = p.v + ((int64_t)b * L + k0) * p.v_pitch + h * kHd;
+    if (lo) {
+      stage_tile<true>(kg, p.k_pitch, k_valid, 128, s_kh, s_kl);
+      stage_tile<true>(vg, p.v_pitch, k_valid, 128, s_vh, s_vl);
+    } else {
+      stage_tile<false>(kg, p.k_pitch, k_valid, 128, s_kh, 0);
+      stage_tile<false>(vg, p.v_pitch, k_valid, 128, s_vh, 0);
+    }
+    for (int q0 = 0; q0 < L; q0 += 128) {
+      const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
+      const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * kHd;
+      const float* dg = p.dout + ((int64_t)b * L + q0) * p.do_pitch + h * kHd;
+      if (lo) {
+        stage_tile<true>(qg, p.q_pitch, q_valid, 128, s_qh, s_ql);
+        stage_tile<true>(dg, p.do_pitch, q_valid, 128, s_dh, s_dl);
+      } else {
+        stage_tile<false>(qg, p.q_pitch, q_valid, 128, s_qh, 0);
+        stage_tile<false>(dg, p.do_pitch, q_valid, 128, s_dh, 0);
+      }
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tcgen05_fence_after();
+        const uint32_t idesc = make_idesc_rt(128, false, false);
+        // S = Q K^T, dP = dO V^T
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t ah = which ? s_dh : s_qh, al = which ? s_dl : s_ql, bh_ = which ? s_vh : s_kh, bl = which ? s_vl : s_kl;
+          const uint32_t td = which ? t_dp : t_s;
+          uint32_t acc = 0;
+          for (int term = 0; term < p.terms; ++term) {
+            const uint64_t da = make_smem_desc_kmajor_sw128(term == 1 ? al : ah), db = make_smem_desc_kmajor_sw128(term == 2 ? bl : bh_);
+#pragma unroll
+            for (int j = 0; j < kHd / UMMA_K; ++j) {
+              umma_bf16(td, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, acc);
+              acc = 1;
+            }
+          }
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tcgen05_fence_after();
+
+      // ---- this thread owns query q0 + row: P (after dropout) and dS for the 128 keys of this tile ----
+      const int q = q0 + row;
+      const bool q_ok = q < L;
+      // delta = sum_d dO[q,d] * O[q,d] over this head's 64 columns (row-sum of P .* dP), lse of this query
+      float delta = 0.f, lse2 = 0.f;
+      if (q_ok) {
+        const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * kHd);
+        const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * kHd);
+#pragma unroll
+        for (int j = 0; j < kHd / 4; ++j) {
+          const float4 x = __ldg(po + j), y = __ldg(pd + j);
+          delta += (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w);
+        }
+        lse2 = p.lse[(int64_t)bh * L + q] * 1.4426950408889634f;
+      }
+      const uint32_t row_key = drop_row_key(seed_lo, (uint32_t)(bh * L + q));
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        float s[32], dp[32];
+        ld_row32(t_s + lane_off + (uint32_t)(ch * 32), s);
+        ld_row32(t_dp + lane_off + (uint32_t)(ch * 32), dp);
+        const uint32_t vb = s_valid[(k0 >> 5) + ch];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = q_ok && ((vb >> j) & 1u);
+          const float pj = ok ? exp2f(s[j] * c2 - lse2) : 0.f;
+          float keep = 1.f;
+          if (p.drop_thresh != 0u) keep = drop_hash(row_key, seed_hi, (uint32_t)(k0 + ch * 32 + j)) >= p.drop_thresh ? p.inv_keep : 0.f;
+          s[j] = pj * keep;                                   // dropped probabilities (dV operand)
+          dp[j] = pj * (dp[j] * keep - delta) * p.scale;      // dS (dQ / dK operand)
+        }
+        store_row32_bf16(s_p, row, ch, s);
+        if (lo) {
+          st_row32(t_s + lane_off + (uint32_t)(ch * 32), s);  // fp32 probabilities stay in TMEM for the lo pass
+          store_row32_bf16_hilo(s_ds, s_dsl, row, ch, dp);
+        } else {
+          store_row32_bf16(s_ds, row, ch, dp);
+        }
+      }
+      if (lo) tmem_st_wait();
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        tcgen05_fence_after();
+        const uint32_t idesc_q = make_idesc_rt(kHd, false, true);  // A K-major (dS), B MN-major (K tile)
+        const uint32_t idesc_t = make_idesc_rt(kHd, true, true);   // A MN-major (dS^T / P^T), B MN-major (Q / dO)
+        const int nt = lo ? 2 : 1;
+        // dQ(tile) = dS K       (contraction over the 128 keys); terms hi*hi, lo*hi, hi*lo
+        uint32_t acc = 0;
+        for (int term = 0; term < p.terms; ++term) {
+          const uint32_t sa = term == 1 ? s_dsl : s_ds, sb = term == 2 ? s_kl : s_kh;
+          for (int j = 0; j < 128 / UMMA_K; ++j) {
+            const uint64_t da = make_smem_desc_kmajor_sw128(sa + (uint32_t)(j >> 2) * T + (uint32_t)(j & 3) * 32u);
+            const uint64_t db = make_smem_desc_mnmajor_sw128(sb + (uint32_t)j * 2048u, 8192);
+            umma_bf16(t_dq, da, db, idesc_q, acc);
+            acc = 1;
+          }
+        }
+        // dK += dS^T Q (hi*hi, lo*hi, hi*lo), dV += P_hi^T dO (dO hi/lo; the P_lo term follows below)
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t td = which ? t_dv : t_dk;
+          uint32_t acc2 = q0 > 0 ? 1u : 0u;
+          const int nterm = which ? nt : p.terms;
+          for (int term = 0; term < nterm; ++term) {
+            const uint32_t sa = which ? s_p : (term == 1 ? s_dsl : s_ds);
+            const uint32_t sb = which ? (term ? s_dl : s_dh) : (term == 2 ? s_ql : s_qh);
+            for (int j = 0; j < 128 / UMMA_K; ++j) {
+              const uint64_t da = make_smem_desc_mnmajor_sw128(sa + (uint32_t)j * 2048u, T);
+              const uint64_t db = make_smem_desc_mnmajor_sw128(sb + (uint32_t)j * 2048u, 8192);
+              umma_bf16(td, da, db, idesc_t, acc2);
+              acc2 = 1;
+            }
+          }
+        }
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      tcgen05_fence_after();
+      // ---- dQ rows of this query tile: first key tile stores, later key tiles accumulate ----
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float g[32];
+        ld_row32(t_dq + lane_off + (uint32_t)(half * 32), g);
+        if (q_ok) {
+          float4* dst = reinterpret_cast<float4*>(p.dq + ((int64_t)b * L + q) * p.dq_pitch + h * kHd + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+            if (k0 > 0) {
+              const float4 old = dst[j];
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            dst[j] = o;
+          }
+        }
+      }
+      if (lo) {
+        // dV += P_lo^T dO_hi through the same P buffer (all MMAs that read P_hi have completed)
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          float s[32];
+          ld_row32(t_s + lane_off + (uint32_t)(ch * 32), s);
+          store_row32_bf16_residual(s_p, row, ch, s);
+        }
+        fence_proxy_async();
+        tcgen05_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          tcgen05_fence_after();
+          const uint32_t idesc_t = make_idesc_rt(kHd, true, true);
+          for (int j = 0; j < 128 / UMMA_K; ++j) {
+            const uint64_t da = make_smem_desc_mnmajor_sw128(s_p + (uint32_t)j * 2048u, T);
+            const uint64_t db = make_smem_desc_mnmajor_sw128(s_dh + (uint32_t)j * 2048u, 8192);
+            umma_bf16(t_dv, da, db, idesc_t, 1u);
+          }
+          umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        tcgen05_fence_after();
+      }
+      tcgen05_fence_before();
+      __syncthreads();  // Q / dO / P / dS tiles and the S / dP / dQ columns are reused
+      tcgen05_fence_after();
+    }
+    // ---- dK, dV rows of this key tile (thread = key) ----
+    const int kk = k0 + row;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      float* dstbase = which ? p.dv : p.dk;
+      const int64_t pitch = which ? p.dv_pitch : p.dk_pitch;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float g[32];
+        ld_row32((which ? t_dv : t_dk) + lane_off + (uint32_t)(half * 32), g);
+        if (kk < L) {
+          float4* dst = reinterpret_cast<float4*>(dstbase + ((int64_t)b * L + kk) * pitch + h * kHd + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+        }
+      }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+  }
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+static int check_attn_ptr(const void* ptr, int64_t pitch, const char* name) {
+  if (ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & 15u) != 0 || (pitch & 3) != 0) {
+    set_error("atq_attention: %s must be non-null, 16-byte aligned, with pitch %% 4 == 0", name);
+    return ATQ_EINVAL;
+  }
+  return ATQ_OK;
+}
+
+static int fill_common(AttnParams& p, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+                       const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
+                       const unsigned long long* seed, int terms) {
+  if (B <= 0 || H <= 0 || L <= 0 || L > 256) {
+    set_error("atq_attention: needs B, H > 0 and 1 <= L <= 256 (got B=%d H=%d L=%d)", B, H, L);
+    return ATQ_EINVAL;
+  }
+  if (terms != 1 && terms != 3) {
+    set_error("atq_attention: terms must be 1 (bf16) or 3 (hi/lo split)");
+    return ATQ_EINVAL;
+  }
+  if (!(dropout_p >= 0.f && dropout_p < 1.f)) {
+    set_error("atq_attention: dropout_p must be in [0, 1)");
+    return ATQ_EINVAL;
+  }
+  const int64_t width = (int64_t)H * kHd;
+  if (q_pitch < width || k_pitch < width || v_pitch < width) {
+    set_error("atq_attention: row pitch smaller than H * 64");
+    return ATQ_EINVAL;
+  }
+  int r;
+  if ((r = check_attn_ptr(q, q_pitch, "q")) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(k, k_pitch, "k")) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(v, v_pitch, "v")) != ATQ_OK) return r;
+  memset(&p, 0, sizeof(p));
+  p.q = q; p.k = k; p.v = v;
+  p.q_pitch = q_pitch; p.k_pitch = k_pitch; p.v_pitch = v_pitch;
+  p.key_pad = key_padding;
+  p.B = B; p.H = H; p.L = L;
+  p.scale = scale;
+  p.terms = terms;
+  p.seed = seed;
+  if (dropout_p > 0.f) {
+    double t = (double)dropout_p * 4294967296.0;
+    p.drop_thresh = t >= 4294967295.0 ? 4294967295u : (t < 1.0 ? 1u : (uint32_t)t);
+    p.inv_keep = 1.f / (1.f - dropout_p);
+  } else {
+    p.drop_thresh = 0u;
+    p.inv_keep = 1.f;
+  }
+  return ATQ_OK;
+}
+
+}  // namespace atq
+
+using namespace atq;
+
+extern "C" {
+
+int atq_attention_fwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+                      const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
+                      const unsigned long long* seed, int terms, float* out, int64_t out_pitch, float* lse,
+                      atq_stream_t stream_) {
+  AttnParams p;
+  int r;
+  if ((r = fill_common(p, B, H, L, q, q_pitch, k, k_pitch, v, v_pitch, key_padding, scale, dropout_p, seed, terms)) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(out, out_pitch, "out")) != ATQ_OK) return r;
+  ATQ_CHECK_ARG(out_pitch >= (int64_t)H * kHd, "out pitch smaller than H * 64");
+  ATQ_ENSURE_DEVICE(device);
+  p.out = out; p.out_pitch = out_pitch; p.lse = lse;
+  p.NK = (L + 31) / 32 * 32;
+  const int nt = terms == 3 ? 2 : 1;
+  const int p_atoms = (p.NK + 63) / 64;
+  const size_t smem = (size_t)2 * nt * p.NK * 128 + (size_t)nt * kTileBytes + (size_t)p_atoms * kTileBytes + 1024;
+  static bool attr_done[64] = {false};
+  if (!attr_done[device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
+    if (e != cudaSuccess) {
+      set_error("atq_attention_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return ATQ_ECUDA;
+    }
+    attr_done[device & 63] = true;
+  }
+  if (smem > (size_t)(227 * 1024 - 512)) {
+    set_error("atq_attention_fwd: shared memory %zu exceeds the per-CTA limit", smem);
+    return ATQ_EINVAL;
+  }
+  attention_fwd_kernel<<<B * H, kAttThreads, smem, (cudaStream_t)stream_>>>(p);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_attention_bwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+                      const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
+                      const unsigned long long* seed, int terms, const float* out, int64_t out_pitch, const float* dout,
+                      int64_t dout_pitch, const float* lse, float* dq, int64_t dq_pitch, float* dk, int64_t dk_pitch,
+                      float* dv, int64_t dv_pitch, atq_stream_t stream_) {
+  AttnParams p;
+  int r;
+  if ((r = fill_common(p, B, H, L, q, q_pitch, k, k_pitch, v, v_pitch, key_padding, scale, dropout_p, seed, terms)) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(out, out_pitch, "out")) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(dout, dout_pitch, "dout")) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(dq, dq_pitch, "dq")) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(dk, dk_pitch, "dk")) != ATQ_OK) return r;
+  if ((r = check_attn_ptr(dv, dv_pitch, "dv")) != ATQ_OK) return r;
+  ATQ_CHECK_ARG(lse != nullptr, "lse is null");
+  const int64_t width = (int64_t)H * kHd;
+  ATQ_CHECK_ARG(out_pitch >= width && dout_pitch >= width && dq_pitch >= width && dk_pitch >= width && dv_pitch >= width,
+                "row pitch smaller than H * 64");
+  ATQ_ENSURE_DEVICE(device);
+  p.o = out; p.o_pitch = out_pitch; p.dout = dout; p.do_pitch = dout_pitch;
+  p.lse = const_cast<float*>(lse);
+  p.dq = dq; p.dk = dk; p.dv = dv;
+  p.dq_pitch = dq_pitch; p.dk_pitch = dk_pitch; p.dv_pitch = dv_pitch;
+  p.NK = 128;
+  const size_t smem = (size_t)14 * kTileBytes + 1024;
+  static bool attr_done[64] = {false};
+  if (!attr_done[device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("atq_attention_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return ATQ_ECUDA;
+    }
+    attr_done[device & 63] = true;
+  }
+  attention_bwd_kernel<<<B * H, kAttThreads, smem, (cudaStream_t)stream_>>>(p);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+}  // extern "C"

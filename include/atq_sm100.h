@@ -206,6 +206,25 @@ size_t atq_workspace_bytes_colsum(int64_t rows, int64_t cols);
 int atq_colsum_f32(int device, const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
                    void* ws, size_t ws_bytes, atq_stream_t stream);
 
+/* ---- fused attention core -------------------------------------------------------
+ * out = dropout(softmax(scale * q k^T + key_padding)) v per (batch, head); replaces the explicit
+ * matmul / masked_fill / softmax / dropout / matmul of models/text_encoder.py:117-163 and its autograd
+ * backward.  q, k, v, out, dout, dq, dk, dv: fp32 [B*L, pitch] with head h in columns [64h, 64h+64)
+ * (head_dim 64, 1 <= L <= 256, 16-byte aligned, pitch % 4 == 0) - the layout the q/k/v projections
+ * write, no head transposes.  key_padding: [B, L] bytes, non-zero = masked key (nullable).
+ * lse: [B*H, L] log-sum-exp of the scaled masked scores (forward output, backward input).
+ * seed: device scalar (nullable = 0) for the counter-based dropout hash; the backward call must pass
+ * the same seed / dropout_p.  terms: 3 = bf16 hi/lo operand split (parity), 1 = bf16 (fast). */
+int atq_attention_fwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+                      const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
+                      const unsigned long long* seed, int terms, float* out, int64_t out_pitch, float* lse,
+                      atq_stream_t stream);
+int atq_attention_bwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+                      const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
+                      const unsigned long long* seed, int terms, const float* out, int64_t out_pitch, const float* dout,
+                      int64_t dout_pitch, const float* lse, float* dq, int64_t dq_pitch, float* dk, int64_t dk_pitch,
+                      float* dv, int64_t dv_pitch, atq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
