@@ -12,6 +12,7 @@ from .routing import apply_selective_routing, SelectiveGradientRouting
 from .precision_boost import ResidualPrecisionBoostLinear
 from ._engine import (set_gemm_mode, get_gemm_mode, set_ste, set_packed_gemm, prepare_quantization,
                       notify_weights_changed)
+from .attention import attention_core, supported as attention_core_supported
 
 __all__ = [
     'adaptive_ternary_quantization',

@@ -53,6 +53,9 @@ class TernaryAttention(nn.Module):
         self.attention_scale = 1.0 / math.sqrt(self.head_dim)
         self.dropout = nn.Dropout(dropout)
         self.pre_layer_norm = nn.LayerNorm(embed_dim)
+        # the B200 package exports a fused attention core (atq/attention.py); the CPU oracle layers do not
+        self._core = getattr(layers, "attention_core", None)
+        self._core_ok = getattr(layers, "attention_core_supported", None)
 
     def update_sparsity(self, progress):
         s = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
@@ -64,6 +67,11 @@ class TernaryAttention(nn.Module):
         query = self.pre_layer_norm(query)
         b = query.size(0)
         q, k, v = self.q_proj(query), self.k_proj(key), self.v_proj(value)
+        if (FUSED_ATTENTION_CORE and self._core is not None and q.is_cuda
+                and self._core_ok(self.embed_dim, self.num_heads, q.size(1))):
+            # own tcgen05 kernels: q/k/v stay in the [B, L, E] layout the projections wrote
+            out = self._core(q, k, v, self.num_heads, key_padding_mask, self.attention_scale, self.dropout.p, self.training)
+            return self.out_proj(out) + 0.1 * query
         q = q.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
         k = k.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
         v = v.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
