@@ -104,19 +104,25 @@ def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads:
 
 
 def dropout_keep_mask(seed: int, batch: int, num_heads: int, seq_len: int, dropout_p: float):
-    """Host restatement of the kernels' counter-based dropout hash (tests): bool [B, H, L, L], True = kept."""
+    """Host restatement of the kernels' counter-based dropout hash (tests): (keep bool [B, H, L, L], effective
+    drop rate).  One 32-bit hash per pair of keys (2k, 2k+1) of a (batch, head, query) row: low / high 16 bits
+    against the 16-bit threshold round(p * 65536)."""
     import numpy as np
     if dropout_p <= 0:
-        return np.ones((batch, num_heads, seq_len, seq_len), dtype=bool)
-    t = dropout_p * 4294967296.0
-    thresh = np.uint32(4294967295 if t >= 4294967295.0 else (1 if t < 1.0 else int(t)))
+        return np.ones((batch, num_heads, seq_len, seq_len), dtype=bool), 0.0
+    thresh = min(max(int(dropout_p * 65536.0 + 0.5), 1), 65535)
     seed_lo, seed_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    pairs = (seq_len + 1) // 2
     with np.errstate(over="ignore"):
         row_id = np.arange(batch * num_heads * seq_len, dtype=np.uint32)
         x = (row_id * np.uint32(0x9E3779B1)) ^ seed_lo
         x ^= x >> np.uint32(16); x *= np.uint32(0x85EBCA6B); x ^= x >> np.uint32(13)
-        key = np.arange(seq_len, dtype=np.uint32)
-        y = x[:, None] + key[None, :] * np.uint32(0xC2B2AE35) + seed_hi
-        y ^= y >> np.uint32(16); y *= np.uint32(0x85EBCA6B); y ^= y >> np.uint32(13)
-        y *= np.uint32(0xC2B2AE35); y ^= y >> np.uint32(16)
-    return (y >= thresh).reshape(batch, num_heads, seq_len, seq_len)
+        x += seed_hi
+        pair = np.arange(pairs, dtype=np.uint32)
+        y = x[:, None] + pair[None, :] * np.uint32(0xC2B2AE35)
+        y ^= y >> np.uint32(16); y *= np.uint32(0x7FEB352D); y ^= y >> np.uint32(15)
+        y *= np.uint32(0x846CA68B); y ^= y >> np.uint32(16)
+    keep = np.empty((row_id.size, 2 * pairs), dtype=bool)
+    keep[:, 0::2] = (y & np.uint32(0xFFFF)) >= thresh
+    keep[:, 1::2] = (y >> np.uint32(16)) >= thresh
+    return keep[:, :seq_len].reshape(batch, num_heads, seq_len, seq_len), thresh / 65536.0

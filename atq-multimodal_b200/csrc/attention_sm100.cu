@@ -24,7 +24,7 @@
 namespace atq {
 
 constexpr int kHd = 64;          // head dim
-constexpr int kAttThreads = 128;
+constexpr int kAttThreads = 256; // 8 warps: warps w and w+4 share TMEM lane quarter w & 3 and split the columns
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
 
 struct AttnParams {
@@ -34,10 +34,10 @@ struct AttnParams {
   float* out;
   int64_t out_pitch;
   float* lse;  // [B*H, L] log-sum-exp of the scaled, masked scores
-  int B, H, L, NK;  // NK = L rounded up to 32 (forward) / key tile 128 (backward)
+  int B, H, L, NK;  // NK = L rounded up to 32 (forward)
   float scale;
-  uint32_t drop_thresh;  // keep iff hash >= thresh; 0 = no dropout
-  float inv_keep;
+  uint32_t drop_thresh;  // 16-bit threshold: keep iff hash16 >= thresh; 0 = no dropout
+  float inv_keep;        // 1 / (1 - thresh / 65536)
   const unsigned long long* seed;  // device scalar, nullable (= 0)
   int terms;  // 3 = hi/lo split (parity), 1 = bf16 only (fast)
   // backward
@@ -47,18 +47,32 @@ struct AttnParams {
   int64_t dq_pitch, dk_pitch, dv_pitch;
 };
 
-__device__ __forceinline__ uint32_t drop_row_key(uint32_t seed_lo, uint32_t row_id) {
+// Dropout: one 32-bit hash per PAIR of keys (2k, 2k+1) of a (batch, head, query) row; key 2k uses the low 16
+// bits, key 2k+1 the high 16 bits.  atq/attention.py:dropout_keep_mask restates it for the tests.
+__device__ __forceinline__ uint32_t drop_row_key(uint32_t seed_lo, uint32_t seed_hi, uint32_t row_id) {
   uint32_t x = (row_id * 0x9E3779B1u) ^ seed_lo;
   x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13;
-  return x;
+  return x + seed_hi;
 }
-__device__ __forceinline__ uint32_t drop_hash(uint32_t row_key, uint32_t seed_hi, uint32_t key) {
-  uint32_t x = row_key + key * 0xC2B2AE35u + seed_hi;
-  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+__device__ __forceinline__ uint32_t drop_hash_pair(uint32_t row_key, uint32_t pair) {
+  uint32_t x = row_key + pair * 0xC2B2AE35u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
   return x;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(uint16_t lo_elem, uint16_t hi_elem) { return (uint32_t)lo_elem | ((uint32_t)hi_elem << 16); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two floats -> packed bf16x2 (a in the low half), one cvt instruction
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // fp32 [rows_valid x 64] (row pitch in floats, 16-byte aligned rows) -> bf16 hi (+ lo) tiles of rows_total
 // swizzled 128-byte rows; rows >= rows_valid become zeros.  8 threads per row (32 B of fp32 each).
@@ -66,7 +80,7 @@ template <bool LO>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t pitch, int rows_valid, int rows_total,
                                            uint32_t s_hi, uint32_t s_lo) {
   const int c = threadIdx.x & 7;
-  constexpr int kRowsPerPass = kAttThreads / 8;  // 16
+  constexpr int kRowsPerPass = kAttThreads / 8;  // 32
   for (int r0 = threadIdx.x >> 3; r0 < rows_total; r0 += 4 * kRowsPerPass) {
     float4 a[4], b[4];
 #pragma unroll
@@ -86,12 +100,15 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_
       const int r = r0 + i * kRowsPerPass;
       if (r < rows_total) {
         const float x[8] = {a[i].x, a[i].y, a[i].z, a[i].w, b[i].x, b[i].y, b[i].z, b[i].w};
-        uint16_t h[8], l[8];
+        uint32_t h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) split_bf16(x[j], h[j], l[j]);
+        for (int j = 0; j < 4; ++j) {
+          h[j] = pack2_bf16(x[2 * j], x[2 * j + 1]);
+          if (LO) l[j] = pack2_bf16(x[2 * j] - bf16lo_f(h[j]), x[2 * j + 1] - bf16hi_f(h[j]));
+        }
         const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4);
-        st_shared_v4(s_hi + off, make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7])));
-        if (LO) st_shared_v4(s_lo + off, make_uint4(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]), pack_bf16x2(l[4], l[5]), pack_bf16x2(l[6], l[7])));
+        st_shared_v4(s_hi + off, make_uint4(h[0], h[1], h[2], h[3]));
+        if (LO) st_shared_v4(s_lo + off, make_uint4(l[0], l[1], l[2], l[3]));
       }
     }
   }
@@ -104,28 +121,6 @@ __device__ __forceinline__ void ld_row32(uint32_t taddr, float (&f)[32]) {
   tmem_ld_wait();
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(r[j]);
-}
-
-// write 32 bf16 values (keys 32*ch .. 32*ch+31 of row `row`) into a K-major [128 x 64k] atom sequence
-__device__ __forceinline__ void store_row32_bf16(uint32_t base, int row, int ch, const float (&v)[32]) {
-  const uint32_t atom = base + (uint32_t)(ch >> 1) * (uint32_t)kTileBytes + (uint32_t)row * 128u;
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(bf16_bits(v[8 * g + 2 * j]), bf16_bits(v[8 * g + 2 * j + 1]));
-    const uint32_t chunk = (uint32_t)((ch & 1) * 4 + g);
-    st_shared_v4(atom + ((chunk ^ ((uint32_t)row & 7u)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
-  }
-}
-
-// residual of the bf16 rounding: v - bf16(v), rounded to bf16 (second pass of a hi/lo operand that has to go
-// through the same shared-memory buffer)
-__device__ __forceinline__ void store_row32_bf16_residual(uint32_t base, int row, int ch, const float (&v)[32]) {
-  float r[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) r[j] = v[j] - bf16_bits_to_float(bf16_bits(v[j]));
-  store_row32_bf16(base, row, ch, r);
 }
 
 // this thread's accumulator row: write 32 consecutive TMEM columns back (fp32)
@@ -146,35 +141,35 @@ __device__ __forceinline__ void st_row32(uint32_t taddr, const float (&f)[32]) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// same, as a (hi, lo) pair: v = hi + lo to ~16 mantissa bits
-__device__ __forceinline__ void store_row32_bf16_hilo(uint32_t base_hi, uint32_t base_lo, int row, int ch, const float (&v)[32]) {
-  const uint32_t off = (uint32_t)(ch >> 1) * (uint32_t)kTileBytes + (uint32_t)row * 128u;
+// 32 values of row `row` (keys 32*ch .. 32*ch+31) -> bf16 in a K-major sequence of [128 x 64-key] atoms.
+// KEEP_LO: v[] is replaced by the rounding residual v - bf16(v) (the lo operand of a later pass).
+template <bool KEEP_LO>
+__device__ __forceinline__ void store_row32_bf16(uint32_t base, int row, int ch, float (&v)[32]) {
+  const uint32_t atom = base + (uint32_t)(ch >> 1) * (uint32_t)kTileBytes + (uint32_t)row * 128u;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    uint32_t wh[4], wl[4];
+    uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint16_t h0, l0, h1, l1;
-      split_bf16(v[8 * g + 2 * j], h0, l0);
-      split_bf16(v[8 * g + 2 * j + 1], h1, l1);
-      wh[j] = pack_bf16x2(h0, h1);
-      wl[j] = pack_bf16x2(l0, l1);
+      const int e = 8 * g + 2 * j;
+      w[j] = pack2_bf16(v[e], v[e + 1]);
+      if (KEEP_LO) {
+        v[e] -= bf16lo_f(w[j]);
+        v[e + 1] -= bf16hi_f(w[j]);
+      }
     }
-    const uint32_t chunk = ((uint32_t)((ch & 1) * 4 + g) ^ ((uint32_t)row & 7u)) << 4;
-    st_shared_v4(base_hi + off + chunk, make_uint4(wh[0], wh[1], wh[2], wh[3]));
-    st_shared_v4(base_lo + off + chunk, make_uint4(wl[0], wl[1], wl[2], wl[3]));
+    const uint32_t chunk = (uint32_t)((ch & 1) * 4 + g);
+    st_shared_v4(atom + ((chunk ^ ((uint32_t)row & 7u)) << 4), make_uint4(w[0], w[1], w[2], w[3]));
   }
 }
 
 // key validity bits (key < L and not padded) for up to 256 keys -> s_valid[8]
 __device__ __forceinline__ void build_valid_bits(const AttnParams& p, int b, uint32_t* s_valid) {
-  for (int k0 = 0; k0 < 256; k0 += kAttThreads) {
-    const int k = k0 + (int)threadIdx.x;
-    bool ok = k < p.L;
-    if (ok && p.key_pad != nullptr) ok = p.key_pad[(int64_t)b * p.L + k] == 0;
-    const uint32_t bits = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0) s_valid[k >> 5] = bits;
-  }
+  const int k = (int)threadIdx.x;  // kAttThreads == 256
+  bool ok = k < p.L;
+  if (ok && p.key_pad != nullptr) ok = p.key_pad[(int64_t)b * p.L + k] == 0;
+  const uint32_t bits = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0) s_valid[k >> 5] = bits;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -194,8 +189,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_valid[8];
+  __shared__ float s_red[2][128];  // row max / row sum partials of the two column halves
   const uint32_t bar = smem_u32(&s_bar);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int half = warp >> 2;               // column half this warp works on
+  const int row = threadIdx.x & 127;        // accumulator row = TMEM lane
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int L = p.L;
 
@@ -219,10 +217,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
   const uint32_t t_s = tmem, t_o = tmem + 256u;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const unsigned long long seed = p.seed != nullptr ? *p.seed : 0ull;
-  const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
   const float c2 = p.scale * 1.4426950408889634f;
+  const int nch = NK / 32;
+  const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
   uint32_t phase = 0;
 
   for (int q0 = 0; q0 < L; q0 += 128) {
@@ -252,36 +251,58 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
     phase ^= 1u;
     tcgen05_fence_after();
 
-    // ---- softmax: this thread owns query q0 + threadIdx.x ----
-    const int row = threadIdx.x;
+    // ---- softmax: query q0 + row; this warp covers key chunks [ch_lo, ch_hi) ----
     const uint32_t t_row = t_s + lane_off;
     float m = -INFINITY;
-    for (int ch = 0; ch < NK / 32; ++ch) {
+    for (int ch = ch_lo; ch < ch_hi; ++ch) {
       float s[32];
       ld_row32(t_row + (uint32_t)(ch * 32), s);
       const uint32_t vb = s_valid[ch];
+      if (vb == 0xffffffffu) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if ((vb >> j) & 1u) m = fmaxf(m, s[j]);
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, s[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if ((vb >> j) & 1u) m = fmaxf(m, s[j]);
+      }
     }
+    s_red[half][row] = m;
+    __syncthreads();
+    m = fmaxf(s_red[0][row], s_red[1][row]);
     if (m == -INFINITY) m = 0.f;  // every key masked: probabilities are all zero below
-    const uint32_t row_key = drop_row_key(seed_lo, (uint32_t)(bh * L + q0 + row));
+    __syncthreads();              // s_red is reused for the row sums
+    const float mc = m * c2;
+    const uint32_t row_key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * L + q0 + row));
     float sum = 0.f;
-    for (int ch = 0; ch < NK / 32; ++ch) {
+    for (int ch = ch_lo; ch < ch_hi; ++ch) {
       float s[32];
       ld_row32(t_row + (uint32_t)(ch * 32), s);
       const uint32_t vb = s_valid[ch];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        float pj = ((vb >> j) & 1u) ? exp2f((s[j] - m) * c2) : 0.f;
+        float pj = ex2_approx(fmaf(s[j], c2, -mc));
+        if (vb != 0xffffffffu) pj = ((vb >> j) & 1u) ? pj : 0.f;
         sum += pj;
-        if (p.drop_thresh != 0u) pj = drop_hash(row_key, seed_hi, (uint32_t)(ch * 32 + j)) >= p.drop_thresh ? pj * p.inv_keep : 0.f;
         s[j] = pj;
       }
-      store_row32_bf16(s_p, row, ch, s);
-      if (lo) st_row32(t_row + (uint32_t)(ch * 32), s);  // keep the fp32 probabilities for the lo pass
+      if (p.drop_thresh != 0u) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t hsh = drop_hash_pair(row_key, (uint32_t)(ch * 16 + (j >> 1)));
+          s[j] = (hsh & 0xFFFFu) >= p.drop_thresh ? s[j] * p.inv_keep : 0.f;
+          s[j + 1] = (hsh >> 16) >= p.drop_thresh ? s[j + 1] * p.inv_keep : 0.f;
+        }
+      }
+      if (lo) {
+        store_row32_bf16<true>(s_p, row, ch, s);        // P_hi to shared memory, s[] <- rounding residual
+        st_row32(t_row + (uint32_t)(ch * 32), s);       // residual stays in TMEM for the lo pass
+      } else {
+        store_row32_bf16<false>(s_p, row, ch, s);
+      }
     }
     if (lo) tmem_st_wait();
+    s_red[half][row] = sum;
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
@@ -301,15 +322,16 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       }
       umma_commit(bar);
     }
+    sum = s_red[0][row] + s_red[1][row];
     mbar_wait(bar, phase);
     phase ^= 1u;
     tcgen05_fence_after();
     if (lo) {
-      // second pass through the same P buffer: P_lo = p - bf16(p) (a single bf16 P leaves ~3e-3 absolute error)
-      for (int ch = 0; ch < NK / 32; ++ch) {
+      // second pass through the same P buffer: P_lo (a single bf16 P leaves ~3e-3 absolute error in P V)
+      for (int ch = ch_lo; ch < ch_hi; ++ch) {
         float s[32];
         ld_row32(t_row + (uint32_t)(ch * 32), s);
-        store_row32_bf16_residual(s_p, row, ch, s);
+        store_row32_bf16<false>(s_p, row, ch, s);
       }
       fence_proxy_async();
       tcgen05_fence_before();
@@ -329,11 +351,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       tcgen05_fence_after();
     }
 
-    // ---- epilogue: normalise and store this query's 64 outputs ----
+    // ---- epilogue: normalise and store; this warp writes output columns [32 half, 32 half + 32) ----
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
     const int q = q0 + row;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    {
       float o[32];
       ld_row32(t_o + lane_off + (uint32_t)(half * 32), o);
       if (q < L) {
@@ -342,13 +363,12 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
       }
     }
-    if (q < L && p.lse != nullptr) p.lse[(int64_t)bh * L + q] = sum > 0.f ? m * p.scale + logf(sum) : -INFINITY;
+    if (half == 0 && q < L && p.lse != nullptr) p.lse[(int64_t)bh * L + q] = sum > 0.f ? m * p.scale + logf(sum) : -INFINITY;
     tcgen05_fence_before();
-    __syncthreads();  // TMEM and the Q / P tiles are reused by the next query tile
+    __syncthreads();  // TMEM, s_red and the Q / P tiles are reused by the next query tile
     tcgen05_fence_after();
   }
   if (warp == 0) tmem_dealloc<512>(tmem);
-  (void)lane;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -356,7 +376,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
 // ------------------------------------------------------------------------------------------
 // shared memory (1024-aligned 16 KB tiles): K hi, K lo, V hi, V lo, Q hi, Q lo, dO hi, dO lo, then P, dS hi and
 // dS lo (two 64-key atoms each; dS carries a lo part because dQ / dK are sums of dS-weighted rows and a single
-// bf16 dS leaves ~3e-3 absolute error, above the 1e-3 tolerance).  TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448).
+// bf16 dS leaves ~3e-3 absolute error, above the 1e-3 tolerance).
+// TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448).
 __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -368,8 +389,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_valid[8];
+  __shared__ float s_red[2][128];  // partial delta of the two column halves
   const uint32_t bar = smem_u32(&s_bar);
   const int warp = threadIdx.x >> 5;
+  const int half = warp >> 2;
+  const int row = threadIdx.x & 127;
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int L = p.L;
 
@@ -384,11 +408,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
   const uint32_t t_s = tmem, t_dp = tmem + 128u, t_dq = tmem + 256u, t_dk = tmem + 320u, t_dv = tmem + 384u;
-  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const unsigned long long seed = p.seed != nullptr ? *p.seed : 0ull;
-  const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
   const float c2 = p.scale * 1.4426950408889634f;
-  const int row = threadIdx.x;
   uint32_t phase = 0;
 
   for (int k0 = 0; k0 < L; k0 += 128) {
@@ -413,6 +435,22 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         stage_tile<false>(qg, p.q_pitch, q_valid, 128, s_qh, 0);
         stage_tile<false>(dg, p.do_pitch, q_valid, 128, s_dh, 0);
       }
+      // delta = sum_d dO[q,d] * O[q,d] over this head (row-sum of P .* dP): each column half adds 32 columns
+      const int q = q0 + row;
+      const bool q_ok = q < L;
+      {
+        float d = 0.f;
+        if (q_ok) {
+          const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * kHd + half * 32);
+          const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * kHd + half * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = __ldg(po + j), y = __ldg(pd + j);
+            d += (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w);
+          }
+        }
+        s_red[half][row] = d;
+      }
       fence_proxy_async();
       tcgen05_fence_before();
       __syncthreads();
@@ -435,47 +473,49 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         }
         umma_commit(bar);
       }
+      const float delta = s_red[0][row] + s_red[1][row];
+      const float lse2 = q_ok ? p.lse[(int64_t)bh * L + q] * 1.4426950408889634f : 0.f;
+      const uint32_t row_key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * L + q));
       mbar_wait(bar, phase);
       phase ^= 1u;
       tcgen05_fence_after();
 
-      // ---- this thread owns query q0 + row: P (after dropout) and dS for the 128 keys of this tile ----
-      const int q = q0 + row;
-      const bool q_ok = q < L;
-      // delta = sum_d dO[q,d] * O[q,d] over this head's 64 columns (row-sum of P .* dP), lse of this query
-      float delta = 0.f, lse2 = 0.f;
-      if (q_ok) {
-        const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * kHd);
-        const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * kHd);
-#pragma unroll
-        for (int j = 0; j < kHd / 4; ++j) {
-          const float4 x = __ldg(po + j), y = __ldg(pd + j);
-          delta += (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w);
-        }
-        lse2 = p.lse[(int64_t)bh * L + q] * 1.4426950408889634f;
-      }
-      const uint32_t row_key = drop_row_key(seed_lo, (uint32_t)(bh * L + q));
+      // ---- query q0 + row, key chunks [2 half, 2 half + 2): P (after dropout) and dS ----
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
         float s[32], dp[32];
         ld_row32(t_s + lane_off + (uint32_t)(ch * 32), s);
         ld_row32(t_dp + lane_off + (uint32_t)(ch * 32), dp);
-        const uint32_t vb = s_valid[(k0 >> 5) + ch];
+        const uint32_t vb = q_ok ? s_valid[(k0 >> 5) + ch] : 0u;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const bool ok = q_ok && ((vb >> j) & 1u);
-          const float pj = ok ? exp2f(s[j] * c2 - lse2) : 0.f;
-          float keep = 1.f;
-          if (p.drop_thresh != 0u) keep = drop_hash(row_key, seed_hi, (uint32_t)(k0 + ch * 32 + j)) >= p.drop_thresh ? p.inv_keep : 0.f;
-          s[j] = pj * keep;                                   // dropped probabilities (dV operand)
-          dp[j] = pj * (dp[j] * keep - delta) * p.scale;      // dS (dQ / dK operand)
+          float pj = ex2_approx(fmaf(s[j], c2, -lse2));
+          if (vb != 0xffffffffu) pj = ((vb >> j) & 1u) ? pj : 0.f;
+          s[j] = pj;
         }
-        store_row32_bf16(s_p, row, ch, s);
-        if (lo) {
-          st_row32(t_s + lane_off + (uint32_t)(ch * 32), s);  // fp32 probabilities stay in TMEM for the lo pass
-          store_row32_bf16_hilo(s_ds, s_dsl, row, ch, dp);
+        if (p.drop_thresh != 0u) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t hsh = drop_hash_pair(row_key, (uint32_t)((k0 >> 1) + ch * 16 + (j >> 1)));
+            const float k0f = (hsh & 0xFFFFu) >= p.drop_thresh ? p.inv_keep : 0.f;
+            const float k1f = (hsh >> 16) >= p.drop_thresh ? p.inv_keep : 0.f;
+            dp[j] = s[j] * (dp[j] * k0f - delta) * p.scale;          // dS uses the un-dropped probability
+            dp[j + 1] = s[j + 1] * (dp[j + 1] * k1f - delta) * p.scale;
+            s[j] *= k0f;                                              // dropped probabilities (dV operand)
+            s[j + 1] *= k1f;
+          }
         } else {
-          store_row32_bf16(s_ds, row, ch, dp);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dp[j] = s[j] * (dp[j] - delta) * p.scale;
+        }
+        if (lo) {
+          store_row32_bf16<true>(s_p, row, ch, s);
+          st_row32(t_s + lane_off + (uint32_t)(ch * 32), s);  // P residual stays in TMEM for the lo pass
+          store_row32_bf16<true>(s_ds, row, ch, dp);
+          store_row32_bf16<false>(s_dsl, row, ch, dp);
+        } else {
+          store_row32_bf16<false>(s_p, row, ch, s);
+          store_row32_bf16<false>(s_ds, row, ch, dp);
         }
       }
       if (lo) tmem_st_wait();
@@ -519,9 +559,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
       mbar_wait(bar, phase);
       phase ^= 1u;
       tcgen05_fence_after();
-      // ---- dQ rows of this query tile: first key tile stores, later key tiles accumulate ----
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      // ---- dQ rows of this query tile (columns [32 half, +32)): first key tile stores, later ones accumulate ----
+      {
         float g[32];
         ld_row32(t_dq + lane_off + (uint32_t)(half * 32), g);
         if (q_ok) {
@@ -540,10 +579,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
       if (lo) {
         // dV += P_lo^T dO_hi through the same P buffer (all MMAs that read P_hi have completed)
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
           float s[32];
           ld_row32(t_s + lane_off + (uint32_t)(ch * 32), s);
-          store_row32_bf16_residual(s_p, row, ch, s);
+          store_row32_bf16<false>(s_p, row, ch, s);
         }
         fence_proxy_async();
         tcgen05_fence_before();
@@ -563,24 +602,21 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         tcgen05_fence_after();
       }
       tcgen05_fence_before();
-      __syncthreads();  // Q / dO / P / dS tiles and the S / dP / dQ columns are reused
+      __syncthreads();  // Q / dO / P / dS tiles, s_red and the S / dP / dQ columns are reused
       tcgen05_fence_after();
     }
-    // ---- dK, dV rows of this key tile (thread = key) ----
+    // ---- dK, dV rows of this key tile (thread = key, columns [32 half, +32)) ----
     const int kk = k0 + row;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       float* dstbase = which ? p.dv : p.dk;
       const int64_t pitch = which ? p.dv_pitch : p.dk_pitch;
+      float g[32];
+      ld_row32((which ? t_dv : t_dk) + lane_off + (uint32_t)(half * 32), g);
+      if (kk < L) {
+        float4* dst = reinterpret_cast<float4*>(dstbase + ((int64_t)b * L + kk) * pitch + h * kHd + half * 32);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float g[32];
-        ld_row32((which ? t_dv : t_dk) + lane_off + (uint32_t)(half * 32), g);
-        if (kk < L) {
-          float4* dst = reinterpret_cast<float4*>(dstbase + ((int64_t)b * L + kk) * pitch + h * kHd + half * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-        }
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
       }
     }
     tcgen05_fence_before();
@@ -631,9 +667,11 @@ static int fill_common(AttnParams& p, int B, int H, int L, const float* q, int64
   p.terms = terms;
   p.seed = seed;
   if (dropout_p > 0.f) {
-    double t = (double)dropout_p * 4294967296.0;
-    p.drop_thresh = t >= 4294967295.0 ? 4294967295u : (t < 1.0 ? 1u : (uint32_t)t);
-    p.inv_keep = 1.f / (1.f - dropout_p);
+    int t = (int)((double)dropout_p * 65536.0 + 0.5);  // 16-bit threshold; the effective rate is t / 65536
+    if (t < 1) t = 1;
+    if (t > 65535) t = 65535;
+    p.drop_thresh = (uint32_t)t;
+    p.inv_keep = (float)(1.0 / (1.0 - (double)t / 65536.0));
   } else {
     p.drop_thresh = 0u;
     p.inv_keep = 1.f;
@@ -664,14 +702,14 @@ int atq_attention_fwd(int device, int B, int H, int L, const float* q, int64_t q
   const size_t smem = (size_t)2 * nt * p.NK * 128 + (size_t)nt * kTileBytes + (size_t)p_atoms * kTileBytes + 1024;
   static bool attr_done[64] = {false};
   if (!attr_done[device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 512);
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1280);
     if (e != cudaSuccess) {
       set_error("atq_attention_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return ATQ_ECUDA;
     }
     attr_done[device & 63] = true;
   }
-  if (smem > (size_t)(227 * 1024 - 512)) {
+  if (smem > (size_t)(227 * 1024 - 1280)) {
     set_error("atq_attention_fwd: shared memory %zu exceeds the per-CTA limit", smem);
     return ATQ_EINVAL;
   }

@@ -45,10 +45,12 @@ def _run_case(b, heads, l, p, with_pad, mode, tol):
         qg, kg, vg = (t.to(DEV).requires_grad_(True) for t in (q, k, v))
         out = A.attention_core(qg, kg, vg, heads, None if pad is None else pad.to(DEV), scale, p, True, seed=seed)
         out.backward(dout.to(DEV))
-        keep = torch.from_numpy(A.dropout_keep_mask(seed_val, b, heads, l, p))
+        keep, p_eff = A.dropout_keep_mask(seed_val, b, heads, l, p)
+        keep = torch.from_numpy(keep)
         if p > 0:
             frac = keep.float().mean().item()
-            assert abs(frac - (1 - p)) < 0.02, frac
+            assert abs(p_eff - p) < 1e-4 and abs(frac - (1 - p)) < 0.02, (p_eff, frac)
+            p = p_eff
         qr, kr, vr = (t.double().requires_grad_(True) for t in (q, k, v))
         ref = _reference(qr, kr, vr, heads, pad, scale, keep, p)
         ref.backward(dout.double())
