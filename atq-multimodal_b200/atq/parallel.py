@@ -54,29 +54,51 @@ class FlatGradAllReduce:
     all-reduce per bucket.  After backward the fresh gradients are packed into the buffer with a single
     multi-tensor copy, reduced, and `p.grad` is re-pointed at views of the buffer (no copy back).
     Parameters that never receive a gradient (TernaryLinear.weight, modules off the training path,
-    SURVEY H8) keep grad=None so the optimizer skips them exactly as in the single-process reference."""
+    SURVEY H8) keep grad=None so the optimizer skips them exactly as in the single-process reference.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 256 << 20, group=None):
+    `sparse_masks`: {parameter: mask} for parameters whose gradient is exactly zero
+    outside `mask != 0` on every rank - ResidualPrecisionBoostLinear.weight with its `precision_mask`
+    (dW = G .* mask, atq/precision_boost.py:72; the mask is identical on all ranks).  Only the masked
+    entries travel: they are gathered into the flat buffer, reduced, and scattered back into the dense
+    `weight.grad` (whose other entries stay zero).  `rpb_masks(model)` builds the dictionary."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 256 << 20, group=None,
+                 sparse_masks: Optional[dict] = None):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.flat: Optional[torch.Tensor] = None
         self.active: List[torch.nn.Parameter] = []
         self.views: List[torch.Tensor] = []
+        self.sparse_masks = {id(p): m for p, m in (sparse_masks or {}).items()}
+        self.sparse_idx: List[Optional[torch.Tensor]] = []
+        self._mask_versions = None
+
+    def _versions(self):
+        return tuple((id(m), m._version) for m in self.sparse_masks.values())
 
     def _bind(self):
         self.active = [p for p in self.params if p.grad is not None]
-        total = sum(p.numel() for p in self.active)
-        self.flat = torch.empty(total, dtype=torch.float32, device=self.active[0].device)
+        self.sparse_idx = []
+        for p in self.active:
+            mask = self.sparse_masks.get(id(p))
+            ok = mask is not None and p.is_contiguous() and mask.shape == p.shape
+            self.sparse_idx.append(torch.nonzero(mask.reshape(-1) != 0).reshape(-1) if ok else None)
+        self._mask_versions = self._versions()
+        sizes = [p.numel() if idx is None else idx.numel() for p, idx in zip(self.active, self.sparse_idx)]
+        self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.active[0].device)
         self.views = []
         off = 0
-        for p in self.active:
-            # same sizes AND strides as the parameter (channels-last conv weights stay channels-last:
-            # fused optimizers require param/grad layouts to match); dense tensors only
-            piece = self.flat[off: off + p.numel()]
-            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
-            self.views.append(piece.as_strided(p.size(), p.stride()) if dense else piece.view_as(p))
-            off += p.numel()
+        for p, idx, n in zip(self.active, self.sparse_idx, sizes):
+            piece = self.flat[off: off + n]
+            if idx is not None:
+                self.views.append(piece)  # compact: the masked entries only
+            else:
+                # same sizes AND strides as the parameter (channels-last conv weights stay channels-last:
+                # fused optimizers require param/grad layouts to match); dense tensors only
+                dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+                self.views.append(piece.as_strided(p.size(), p.stride()) if dense else piece.view_as(p))
+            off += n
 
     def zero_grad(self):
         """Drop every gradient so autograd writes fresh tensors (no read-modify-write accumulation)."""
@@ -84,19 +106,36 @@ class FlatGradAllReduce:
             p.grad = None
 
     def reduce(self):
-        if self.flat is None:
-            self._bind()  # first step: discover which parameters this graph produces gradients for
-        grads = []
-        for p, view in zip(self.active, self.views):
+        if self.flat is None or (self.sparse_masks and self._mask_versions != self._versions()):
+            self._bind()  # first step (or a mask was re-initialised): discover the gradients this graph produces
+        dst, grads = [], []
+        for p, view, idx in zip(self.active, self.views, self.sparse_idx):
             if p.grad is None:  # parameter unused this step: contributes zeros
                 view.zero_()
-                grads.append(view)
+            elif idx is not None:
+                torch.index_select(p.grad.view(-1), 0, idx, out=view)  # gather the masked entries
             else:
+                dst.append(view)
                 grads.append(p.grad)
-        torch._foreach_copy_(self.views, grads)  # multi-tensor pack into the flat buffer
+        if dst:
+            torch._foreach_copy_(dst, grads)  # multi-tensor pack into the flat buffer
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
             n = self.flat.numel()
             for start in range(0, n, self.bucket_elems):
                 dist.all_reduce(self.flat[start: min(n, start + self.bucket_elems)], op=dist.ReduceOp.SUM, group=self.group)
-        for p, view in zip(self.active, self.views):
-            p.grad = view
+        for p, view, idx in zip(self.active, self.views, self.sparse_idx):
+            if idx is None:
+                p.grad = view
+            elif p.grad is not None:
+                p.grad.view(-1).index_copy_(0, idx, view)  # scatter the reduced entries back (rest stays zero)
+
+
+def rpb_masks(model: torch.nn.Module) -> dict:
+    """{weight parameter: precision_mask} of every ResidualPrecisionBoostLinear-like module of `model`."""
+    out = {}
+    for m in model.modules():
+        mask = getattr(m, "precision_mask", None)
+        w = getattr(m, "weight", None)
+        if mask is not None and isinstance(w, torch.nn.Parameter) and mask.shape == w.shape:
+            out[w] = mask
+    return out

@@ -230,6 +230,33 @@ def kernel_rooflines(device, peaks, flush, quick=True):
                         "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
                         "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": traffic,
                         "algorithmic_bytes": 2 * N * K * (2 if want_lo else 1) + (M * K // 4 if "packed" in bsrc else 2 * M * K) + 4 * N * M})
+    # ---- config 4: fused attention core at the image-tower shape (512 images x 12 heads x 197 tokens, head_dim 64)
+    import atq
+    from atq import attention as A
+    b_, h_, l_ = 512, 12, 197
+    q, k, v = (torch.randn(b_, l_, h_ * 64, device=device, generator=g).requires_grad_(True) for _ in range(3))
+    dout = torch.randn(b_, l_, h_ * 64, device=device, generator=g)
+    seed = torch.tensor([1], dtype=torch.int64, device=device)
+    prev_mode = atq.get_gemm_mode()
+    for mode in ("parity", "fast"):
+        atq.set_gemm_mode(mode)
+        with torch.no_grad():
+            ms_f = _event_time(lambda: A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed), 5, flush)
+        o = A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed)
+
+        def bwd():
+            q.grad = k.grad = v.grad = None
+            o.backward(dout, retain_graph=True)
+        ms_b = _event_time(bwd, 5, flush)
+        for name, ms, fl in (("attention_fwd_kernel", ms_f, 4.0), ("attention_bwd_kernel", ms_b, 10.0)):
+            ach = fl * l_ * l_ * 64 * b_ * h_ / (ms * 1e-3) / 1e12
+            out.append({"kernel": f"{name} {mode}", "workload": f"config4 attention core {b_}x{h_}x{l_}x64, dropout 0.1",
+                        "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
+                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None,
+                        "note": "useful flops 4 (fwd) / 10 (bwd) x L^2 x 64 per head; softmax-issue / phase-latency bound, not tensor bound"})
+        del o
+    atq.set_gemm_mode(prev_mode)
+    del q, k, v, dout
     # ---- config 5: quantize + pack, one 4096x4096 layer (64 MiB fp32; L2 flushed between runs)
     n = M * K
     ms = _event_time(lambda: eng.adaptive_threshold(w, 0.3), 5, flush)
@@ -332,7 +359,9 @@ def run_ours(args, cfg):
     # kernel-bound (and its activations would be held twice by a capture pool), so it runs eagerly
     use_graph = (not args.no_graph) and args.workload == "flickr8k"
     opt = T.make_optimizer(model, cfg, capturable=use_graph, fused=True)
-    sync = parallel.FlatGradAllReduce(model.parameters()) if world > 1 else None
+    sync = None
+    if world > 1:  # --sparse-grads: only the entries under each RPB precision_mask travel
+        sync = parallel.FlatGradAllReduce(model.parameters(), sparse_masks=parallel.rpb_masks(model) if args.sparse_grads else None)
     gather = parallel.gather_embeddings if world > 1 else None
 
     pool = 4
@@ -472,6 +501,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--sparse-grads", action="store_true", help="N>1: all-reduce only the masked entries of RPB weight gradients")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from workloads import train as T

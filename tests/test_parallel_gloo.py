@@ -77,3 +77,51 @@ def test_gather_is_identity_without_process_group():
     x = torch.randn(3, 4, requires_grad=True)
     assert parallel.gather_embeddings(x) is x
     assert parallel.init_from_env() == (0, 1, 0)
+
+
+def _sparse_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from atq import parallel
+    from workloads import models as M
+    parallel.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    L = M.oracle_layers()
+    enc = L.ResidualPrecisionBoostLinear(12, 8, precision_ratio=0.3, sparsity_target=0.2)
+    head = torch.nn.Linear(8, 4)
+    params = list(enc.parameters()) + list(head.parameters())
+    masks = parallel.rpb_masks(torch.nn.Sequential(enc, head))
+    assert list(masks) == [enc.weight]
+    g = torch.Generator().manual_seed(7 + rank)  # different data per rank
+    x = torch.randn(5, 12, generator=g)
+    results = {}
+    for kind, sync in (("dense", parallel.FlatGradAllReduce(params)),
+                       ("sparse", parallel.FlatGradAllReduce(params, sparse_masks=masks))):
+        for _ in range(2):
+            sync.zero_grad()
+            head(enc(x)).square().sum().backward()
+            sync.reduce()
+        results[kind] = [p.grad.clone() for p in params if p.grad is not None]
+        results[kind + "_flat"] = sync.flat.numel()
+    nnz = int((enc.precision_mask != 0).sum())
+    assert results["dense_flat"] - results["sparse_flat"] == enc.weight.numel() - nnz
+    for a, b in zip(results["dense"], results["sparse"]):
+        assert torch.equal(a, b)
+    wg = results["sparse"][0]
+    assert torch.count_nonzero(wg * (1 - enc.precision_mask)) == 0 and torch.count_nonzero(wg) > 0
+    torch.save(results["sparse"], os.path.join(out_dir, f"s{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sparse_rpb_gradient_all_reduce_matches_dense(tmp_path):
+    """only the entries under precision_mask travel; result identical to the dense all-reduce."""
+    world = 2
+    mp.spawn(_sparse_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (torch.load(tmp_path / f"s{r}.pt") for r in range(world))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
