@@ -817,7 +817,7 @@ size_t atq_workspace_bytes_tgemm_dw(int64_t out_features, int64_t in_features, i
 
 int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, int64_t n_tokens,
                         const atq_bf16_operand* dy_t, const atq_bf16_operand* x_t, const float* mask,
-                        const uint8_t* packed_t, float* dw, int64_t dw_pitch, float* dalpha_out, void* ws,
+                        const uint8_t* packed, float* dw, int64_t dw_pitch, float* dalpha_out, void* ws,
                         size_t ws_bytes, atq_stream_t stream_) {
   ATQ_CHECK_ARG(out_features > 0 && in_features > 0 && n_tokens > 0 && dw != nullptr && dw_pitch >= in_features,
                 "bad shape or null output");
@@ -826,7 +826,7 @@ int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, i
   if ((r = check_operand(x_t, "x_t")) != ATQ_OK) return r;
   ATQ_CHECK_ARG(dy_t->pitch >= (dy_t->mn_major ? out_features : n_tokens) && x_t->pitch >= (x_t->mn_major ? in_features : n_tokens),
                 "operand pitch smaller than its contiguous extent");
-  ATQ_CHECK_ARG((packed_t == nullptr) == (dalpha_out == nullptr), "packed_t and dalpha_out go together");
+  ATQ_CHECK_ARG((packed == nullptr) == (dalpha_out == nullptr), "packed and dalpha_out go together");
   ATQ_ENSURE_DEVICE(device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t part_bytes = atq_workspace_bytes_tgemm(out_features, in_features) + 4096;
@@ -843,7 +843,7 @@ int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, i
   int grid = 0;
   if (splits <= 1) {
     p.out = dw; p.out_pitch = dw_pitch;
-    p.mask = mask; p.tern = packed_t;
+    p.mask = mask; p.tern = packed;
     p.partials = dalpha_out ? (float*)ws : nullptr;
     if ((r = dispatch<EPI_MASKED>(dy_t, x_t, p, stream, &grid)) != ATQ_OK) return r;
   } else {
@@ -859,7 +859,7 @@ int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, i
     if (fg > cap) fg = cap;
     if (fg < 1) fg = 1;
     grid = (int)fg;
-    splitk_finalize_masked_kernel<<<grid, 256, 0, stream>>>(slabs, splits, p.split_stride, out_features, in_features, mask, packed_t,
+    splitk_finalize_masked_kernel<<<grid, 256, 0, stream>>>(slabs, splits, p.split_stride, out_features, in_features, mask, packed,
                                                              dw, dw_pitch, dalpha_out ? (float*)ws : nullptr);
     ATQ_LAUNCH_CHECK();
   }

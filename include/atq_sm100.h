@@ -196,7 +196,7 @@ int atq_tgemm_dx(int device, int64_t n_tokens, int64_t in_features, int64_t out_
 size_t atq_workspace_bytes_tgemm_dw(int64_t out_features, int64_t in_features, int64_t n_tokens);
 int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, int64_t n_tokens,
                         const atq_bf16_operand* dy_t, const atq_bf16_operand* x_t,
-                        const float* mask, const uint8_t* packed_t,
+                        const float* mask, const uint8_t* packed /* codec bytes of T [M*K/4], row-major */,
                         float* dw, int64_t dw_pitch, float* dalpha_out,
                         void* ws, size_t ws_bytes, atq_stream_t stream);
 
