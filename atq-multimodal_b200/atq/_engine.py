@@ -518,6 +518,104 @@ class _RPBLinearFn(torch.autograd.Function):
         return dx, dw, dalpha, dbias, None, None
 
 
+def gelu_dropout_split(y: torch.Tensor, dropout_p: float, seed, want_lo: bool):
+    """d = dropout(gelu(y)) as a bf16 (hi, lo|None, pitch) GEMM operand; y contiguous fp32 [rows, cols], cols % 8 == 0."""
+    rows, cols = y.shape
+    dev = nv.device_index(y)
+    hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device)
+    lo = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device) if want_lo else None
+    nv.call("atq_gelu_dropout_split", dev, y.data_ptr(), rows, cols, float(dropout_p), nv.ptr(seed), hi.data_ptr(), nv.ptr(lo),
+            nv.stream_ptr(dev))
+    return hi, lo, cols
+
+
+def gelu_dropout_bwd_split_colsum(g: torch.Tensor, y: torch.Tensor, dropout_p: float, seed, want_lo: bool):
+    """dy = g * keep/(1-p) * gelu'(y) as a bf16 operand + its column sums."""
+    rows, cols = y.shape
+    dev = nv.device_index(y)
+    hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device)
+    lo = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device) if want_lo else None
+    out = torch.empty(cols, dtype=torch.float32, device=y.device)
+    ws = nv.workspace(nv.lib.atq_workspace_bytes_split_colsum(rows, cols), y.device)
+    nv.call("atq_gelu_dropout_bwd_split_colsum", dev, g.data_ptr(), y.data_ptr(), rows, cols, float(dropout_p), nv.ptr(seed),
+            hi.data_ptr(), nv.ptr(lo), out.data_ptr(), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+    return (hi, lo, cols), out
+
+
+class _RPBFFNFn(torch.autograd.Function):
+    """y = linear2(dropout(gelu(linear1(x)))) for two ResidualPrecisionBoostLinear layers
+    (models/text_encoder.py:246): the activation, the dropout and the operand split of the hidden tensor are one
+    streaming kernel per direction, the [tokens, hidden] gelu / dropout outputs never exist in fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w1, alpha1, b1, mask1, ops1, w2, alpha2, b2, mask2, ops2, p, seed):
+        H, K = w1.shape
+        M = w2.shape[0]
+        x2 = nv.require_f32(x, "input").reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        N = x2.shape[0]
+        lo = _use_lo()
+        xa = split_bf16(x2, lo)
+        y1, _ = tgemm(xa, ops1.w, N, H, K, bias=None if b1 is None else b1.detach())
+        da = gelu_dropout_split(y1, p, seed, lo)
+        y2, _ = tgemm(da, ops2.w, N, M, H, bias=None if b2 is None else b2.detach())
+        tensors = [y1, mask1, mask2, xa[0], da[0]] + ([xa[1], da[1]] if lo else [])
+        ctx.save_for_backward(*tensors)
+        ctx.seed = seed
+        ctx.cfg = (N, K, H, M, float(p), lo, xa[2], b1 is not None, b2 is not None)
+        ctx.ops = (ops1.w_t, ops1.packed, ops2.w_t, ops2.packed)
+        ctx.xshape = x.shape
+        return y2.reshape(*x.shape[:-1], M)
+
+    @staticmethod
+    def backward(ctx, gy):
+        N, K, H, M, p, lo, x_pitch, has_b1, has_b2 = ctx.cfg
+        saved = ctx.saved_tensors
+        y1, mask1, mask2 = saved[0], saved[1], saved[2]
+        xa = (saved[3], saved[5] if lo else None, x_pitch)
+        da = (saved[4], saved[6] if lo else None, H)
+        w1_t, packed1, w2_t, packed2 = ctx.ops
+        g2 = nv.require_f32(gy, "grad_output").reshape(-1, M)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        if has_b2:
+            ga2, db2 = split_bf16_colsum(g2, lo)
+        else:
+            ga2, db2 = split_bf16(g2, lo), None
+        dd, _ = tgemm(ga2, w2_t, N, H, M)  # gradient w.r.t. the dropped activations, fp32 [N, H]
+        mk2 = mask2 if mask2.is_contiguous() else mask2.contiguous()
+        dw2, dalpha2 = tgemm_dw_masked(ga2 + (1,), da + (1,), M, H, N, mask=mk2, packed=packed2)
+        g1a, db1 = gelu_dropout_bwd_split_colsum(dd, y1, p, ctx.seed, lo)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx, _ = tgemm(g1a, w1_t, N, K, H)
+            dx = dx.reshape(ctx.xshape)
+        mk1 = mask1 if mask1.is_contiguous() else mask1.contiguous()
+        dw1, dalpha1 = tgemm_dw_masked(g1a + (1,), xa + (1,), H, K, N, mask=mk1, packed=packed1)
+        return (dx, dw1, dalpha1, db1 if has_b1 else None, None, None, dw2, dalpha2, db2, None, None, None, None)
+
+
+def rpb_ffn_supported(l1, l2, x) -> bool:
+    """Both layers ResidualPrecisionBoostLinear-like on CUDA, chained shapes, hidden width % 8 == 0, some tokens."""
+    return (hasattr(l1, "precision_mask") and hasattr(l2, "precision_mask") and x.is_cuda and l1.weight.is_cuda
+            and l1.weight.shape[0] == l2.weight.shape[1] and l1.weight.shape[0] % 8 == 0 and x.numel() > 0
+            and x.shape[-1] == l1.weight.shape[1])
+
+
+def rpb_ffn(l1, l2, x, dropout_p: float = 0.0, training: bool = True, seed=None, threshold_factor=0.05):
+    """linear2(dropout(gelu(linear1(x)))) with the fused activation kernels; l1, l2: ResidualPrecisionBoostLinear."""
+    if not rpb_ffn_supported(l1, l2, x):
+        raise RuntimeError("atq.fused_ffn: needs two chained ResidualPrecisionBoostLinear layers on CUDA (hidden % 8 == 0)")
+    p = float(dropout_p) if training else 0.0
+    if p > 0.0 and seed is None:
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=x.device)
+    ops1 = layer_operands(l1._ops, l1.weight, l1.alpha, l1.precision_mask, l1.sparsity_target, threshold_factor)
+    ops2 = layer_operands(l2._ops, l2.weight, l2.alpha, l2.precision_mask, l2.sparsity_target, threshold_factor)
+    return _RPBFFNFn.apply(x, l1.weight, l1.alpha, l1.bias, l1.precision_mask, ops1,
+                           l2.weight, l2.alpha, l2.bias, l2.precision_mask, ops2, p, seed if p > 0.0 else None)
+
+
 def ternary_linear(x, weight, alpha, bias, cache: LayerOperands, sparsity_target=0.3, threshold_factor=0.05):
     ops = layer_operands(cache, weight, None, None, sparsity_target, threshold_factor)
     return _TernaryLinearFn.apply(x, weight, alpha, bias, ops)

@@ -21,7 +21,7 @@ if not os.path.exists(_LIB_PATH):
         "(or `make -C atq-multimodal_b200/csrc`). The atq package has no CPU or eager fallback.")
 _lib = ctypes.CDLL(_LIB_PATH)
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class BF16Operand(Structure):
@@ -73,6 +73,8 @@ _SIGS = {
                                     _P, _P, c_int64, _P, _P, c_size_t, _P]),
     "atq_workspace_bytes_colsum": (c_size_t, [c_int64, c_int64]),
     "atq_colsum_f32": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "atq_gelu_dropout_split": (c_int, [c_int, _P, c_int64, c_int64, c_float, _P, _P, _P, _P]),
+    "atq_gelu_dropout_bwd_split_colsum": (c_int, [c_int, _P, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
     "atq_attention_fwd": (c_int, [c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_float, c_float,
                                   _P, c_int, _P, c_int64, _P, _P]),
     "atq_attention_bwd": (c_int, [c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_float, c_float,

@@ -47,19 +47,6 @@ struct AttnParams {
   int64_t dq_pitch, dk_pitch, dv_pitch;
 };
 
-// Dropout: one 32-bit hash per PAIR of keys (2k, 2k+1) of a (batch, head, query) row; key 2k uses the low 16
-// bits, key 2k+1 the high 16 bits.  atq/attention.py:dropout_keep_mask restates it for the tests.
-__device__ __forceinline__ uint32_t drop_row_key(uint32_t seed_lo, uint32_t seed_hi, uint32_t row_id) {
-  uint32_t x = (row_id * 0x9E3779B1u) ^ seed_lo;
-  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13;
-  return x + seed_hi;
-}
-__device__ __forceinline__ uint32_t drop_hash_pair(uint32_t row_key, uint32_t pair) {
-  uint32_t x = row_key + pair * 0xC2B2AE35u;
-  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x;
-}
-
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -666,16 +653,7 @@ static int fill_common(AttnParams& p, int B, int H, int L, const float* q, int64
   p.scale = scale;
   p.terms = terms;
   p.seed = seed;
-  if (dropout_p > 0.f) {
-    int t = (int)((double)dropout_p * 65536.0 + 0.5);  // 16-bit threshold; the effective rate is t / 65536
-    if (t < 1) t = 1;
-    if (t > 65535) t = 65535;
-    p.drop_thresh = (uint32_t)t;
-    p.inv_keep = (float)(1.0 / (1.0 - (double)t / 65536.0));
-  } else {
-    p.drop_thresh = 0u;
-    p.inv_keep = 1.f;
-  }
+  dropout_threshold(dropout_p, &p.drop_thresh, &p.inv_keep);  // 16-bit threshold; effective rate thresh / 65536
   return ATQ_OK;
 }
 

@@ -109,4 +109,31 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
   lo = (fabsf(hf) <= 3.3895313892515355e38f) ? bf16_bits(r) : (uint16_t)0;
 }
 
+// Counter-based dropout (shared by the attention kernels and the fused FFN activation): one 32-bit hash per
+// PAIR of consecutive elements (2k, 2k+1) of a row; element 2k uses the low 16 bits, 2k+1 the high 16 bits,
+// kept iff >= the 16-bit threshold round(p * 65536).  atq/attention.py restates it on the host for the tests.
+__device__ __forceinline__ uint32_t drop_row_key(uint32_t seed_lo, uint32_t seed_hi, uint32_t row_id) {
+  uint32_t x = (row_id * 0x9E3779B1u) ^ seed_lo;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13;
+  return x + seed_hi;
+}
+__device__ __forceinline__ uint32_t drop_hash_pair(uint32_t row_key, uint32_t pair) {
+  uint32_t x = row_key + pair * 0xC2B2AE35u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+// 16-bit threshold and 1/(1-p_effective) for a requested rate p (host)
+static inline void dropout_threshold(float p, uint32_t* thresh, float* inv_keep) {
+  if (p > 0.f) {
+    int t = (int)((double)p * 65536.0 + 0.5);
+    if (t < 1) t = 1;
+    if (t > 65535) t = 65535;
+    *thresh = (uint32_t)t;
+    *inv_keep = (float)(1.0 / (1.0 - (double)t / 65536.0));
+  } else {
+    *thresh = 0u;
+    *inv_keep = 1.f;
+  }
+}
+
 }  // namespace atq

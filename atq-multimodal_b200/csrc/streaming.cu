@@ -351,6 +351,81 @@ __global__ void __launch_bounds__(kThreads)
   *reinterpret_cast<float4*>(part + rl * cols + 4 * cg) = acc;
 }
 
+// ------------------------------------------------------------------------------------
+// FFN activation fused with the operand split ("GELU into the FFN epilogue").
+//   forward : d  = dropout(gelu(y))                   -> bf16 (hi, lo) operand of the second FFN GEMM
+//   backward: dy = g .* keep/(1-p) .* gelu'(y)        -> bf16 (hi, lo) operand of the first layer's dX / dW
+//             GEMMs + column sums (its bias gradient)
+// gelu is the exact erf form (F.gelu default, models/text_encoder.py:246).  The dropout mask is never
+// stored: both directions regenerate it from the counter hash of (seed, flat element index).
+// Same lane layout as split_colsum_kernel: a thread owns 4 consecutive columns of every R-th row.
+// ------------------------------------------------------------------------------------
+struct ActParams {
+  uint32_t drop_thresh;  // 0 = no dropout
+  float inv_keep;
+  const unsigned long long* seed;
+};
+
+__device__ __forceinline__ float gelu_fwd(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+}
+
+template <bool BWD, bool HAS_LO>
+__global__ void __launch_bounds__(kThreads)
+    act_split_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t rows, int64_t cols,
+                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ part, int64_t R, const ActParams ap) {
+  const int64_t cg4 = cols >> 2;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= cg4 * R) return;
+  const int64_t cg = t % cg4, rl = t / cg4;
+  uint32_t key = 0;
+  if (ap.drop_thresh != 0u) {
+    const unsigned long long seed = ap.seed != nullptr ? *ap.seed : 0ull;
+    key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), 0x0FF1CEu);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r0 = rl; r0 < rows; r0 += R * kUnroll) {
+    float4 v[kUnroll], w[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      const int64_t r = r0 + j * R;
+      if (r < rows) {
+        v[j] = ldg_stream4(x + r * cols + 4 * cg);
+        if constexpr (BWD) w[j] = ldg_stream4(y + r * cols + 4 * cg);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      const int64_t r = r0 + j * R;
+      if (r >= rows) continue;
+      const int64_t g = r * cg4 + cg;  // float4 group index = flat element index / 4
+      float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
+      if (ap.drop_thresh != 0u) {
+        const uint32_t h0 = drop_hash_pair(key, (uint32_t)(2 * g)), h1 = drop_hash_pair(key, (uint32_t)(2 * g + 1));
+        k0 = (h0 & 0xFFFFu) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+        k1 = (h0 >> 16) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+        k2 = (h1 & 0xFFFFu) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+        k3 = (h1 >> 16) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+      }
+      float4 o;
+      if constexpr (BWD) {
+        o = make_float4(v[j].x * k0 * gelu_grad(w[j].x), v[j].y * k1 * gelu_grad(w[j].y), v[j].z * k2 * gelu_grad(w[j].z),
+                        v[j].w * k3 * gelu_grad(w[j].w));
+      } else {
+        o = make_float4(gelu_fwd(v[j].x) * k0, gelu_fwd(v[j].y) * k1, gelu_fwd(v[j].z) * k2, gelu_fwd(v[j].w) * k3);
+      }
+      uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+      *reinterpret_cast<uint2*>(hi + 4 * g) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+      if constexpr (HAS_LO)
+        *reinterpret_cast<uint2*>(lo + 4 * g) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+      if constexpr (BWD) { acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    }
+  }
+  if constexpr (BWD) *reinterpret_cast<float4*>(part + rl * cols + 4 * cg) = acc;
+}
+
 template <bool HAS_LO>
 __global__ void __launch_bounds__(kThreads)
     split_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
@@ -804,6 +879,53 @@ int atq_split_bf16_colsum(int device, const float* x, int64_t rows, int64_t cols
   const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
   if (lo) split_colsum_kernel<true><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R);
   else split_colsum_kernel<false><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R);
+  ATQ_LAUNCH_CHECK();
+  colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>((const float*)ws, R, cols, colsum_out);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_gelu_dropout_split(int device, const float* y, int64_t rows, int64_t cols, float dropout_p,
+                           const unsigned long long* seed, uint16_t* hi, uint16_t* lo, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(y && hi && rows > 0 && cols > 0, "null pointer or empty shape");
+  ATQ_CHECK_ARG((cols % 8) == 0 && aligned16(y) && aligned16(hi) && (lo == nullptr || aligned16(lo)),
+                "needs cols % 8 == 0 and 16-byte aligned contiguous tensors");
+  ATQ_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && rows * cols < ((int64_t)1 << 33), "dropout_p in [0,1), rows*cols < 2^33");
+  ATQ_ENSURE_DEVICE(device);
+  ActParams ap;
+  dropout_threshold(dropout_p, &ap.drop_thresh, &ap.inv_keep);
+  ap.seed = seed;
+  const int64_t R = split_colsum_lanes(device, rows, cols);
+  const int64_t threads = (cols >> 2) * R;
+  const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (lo) act_split_kernel<false, true><<<grid, kThreads, 0, stream>>>(y, nullptr, rows, cols, hi, lo, nullptr, R, ap);
+  else act_split_kernel<false, false><<<grid, kThreads, 0, stream>>>(y, nullptr, rows, cols, hi, lo, nullptr, R, ap);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y, int64_t rows, int64_t cols, float dropout_p,
+                                      const unsigned long long* seed, uint16_t* hi, uint16_t* lo, float* colsum_out,
+                                      void* ws, size_t ws_bytes, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(g && y && hi && colsum_out && rows > 0 && cols > 0, "null pointer or empty shape");
+  ATQ_CHECK_ARG((cols % 8) == 0 && aligned16(g) && aligned16(y) && aligned16(hi) && (lo == nullptr || aligned16(lo)),
+                "needs cols % 8 == 0 and 16-byte aligned contiguous tensors");
+  ATQ_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && rows * cols < ((int64_t)1 << 33), "dropout_p in [0,1), rows*cols < 2^33");
+  ATQ_ENSURE_DEVICE(device);
+  const int64_t R = split_colsum_lanes(device, rows, cols);
+  if (ws == nullptr || ws_bytes < (size_t)(R * cols * sizeof(float))) {
+    set_error("atq_gelu_dropout_bwd_split_colsum: workspace too small (atq_workspace_bytes_split_colsum)");
+    return ATQ_EWORKSPACE;
+  }
+  ActParams ap;
+  dropout_threshold(dropout_p, &ap.drop_thresh, &ap.inv_keep);
+  ap.seed = seed;
+  const int64_t threads = (cols >> 2) * R;
+  const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (lo) act_split_kernel<true, true><<<grid, kThreads, 0, stream>>>(g, y, rows, cols, hi, lo, (float*)ws, R, ap);
+  else act_split_kernel<true, false><<<grid, kThreads, 0, stream>>>(g, y, rows, cols, hi, lo, (float*)ws, R, ap);
   ATQ_LAUNCH_CHECK();
   colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>((const float*)ws, R, cols, colsum_out);
   ATQ_LAUNCH_CHECK();

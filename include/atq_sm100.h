@@ -225,6 +225,18 @@ int atq_attention_bwd(int device, int B, int H, int L, const float* q, int64_t q
                       int64_t dout_pitch, const float* lse, float* dq, int64_t dq_pitch, float* dk, int64_t dk_pitch,
                       float* dv, int64_t dv_pitch, atq_stream_t stream);
 
+/* ---- FFN activation fused with the operand split (GELU into the FFN epilogue) -----
+ * forward : d = dropout(gelu(y)) (exact erf GELU, models/text_encoder.py:246) written ONLY as the bf16
+ *           (hi, lo) A operand of the second FFN GEMM ([rows, cols], pitch = cols, cols % 8 == 0);
+ * backward: dy = g .* keep/(1-p) .* gelu'(y) as the (hi, lo) operand of the first layer's dX / dW GEMMs plus
+ *           its column sums (bias gradient); ws >= atq_workspace_bytes_split_colsum(rows, cols).
+ * The dropout mask is regenerated from the counter hash of (seed, flat index): pass the same seed / p. */
+int atq_gelu_dropout_split(int device, const float* y, int64_t rows, int64_t cols, float dropout_p,
+                           const unsigned long long* seed, uint16_t* hi, uint16_t* lo, atq_stream_t stream);
+int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y, int64_t rows, int64_t cols, float dropout_p,
+                                      const unsigned long long* seed, uint16_t* hi, uint16_t* lo, float* colsum_out,
+                                      void* ws, size_t ws_bytes, atq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

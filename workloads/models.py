@@ -28,6 +28,8 @@ def _lengths_to_mask(lengths, batch, seq, device):
 # True: the softmax(QK^T)V core of TernaryAttention runs as one fused SDPA kernel (forward) + one (backward)
 # instead of materialising the score tensors; False: the reference's explicit matmul/softmax/dropout sequence.
 FUSED_ATTENTION_CORE = True
+# True: linear2(dropout(gelu(linear1(h)))) of a TernaryBlock runs through atq.fused_ffn when both layers are RPB
+FUSED_FFN = True
 
 
 class TernaryAttention(nn.Module):
@@ -113,6 +115,8 @@ class TernaryBlock(nn.Module):
         self.dropout1 = nn.Dropout(dropout)
         self.dropout2 = nn.Dropout(dropout)
         self.gate = nn.Parameter(torch.ones(1) * 0.8)
+        self._ffn = getattr(layers, "fused_ffn", None)            # B200 package only
+        self._ffn_ok = getattr(layers, "fused_ffn_supported", None)
 
     def update_sparsity(self, progress):
         s = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
@@ -127,7 +131,11 @@ class TernaryBlock(nn.Module):
         gate = torch.sigmoid(self.gate)
         src = src + self.dropout1(h) * gate
         h = self.norm2(src)
-        h = self.linear2(self.dropout(F.gelu(self.linear1(h))))
+        if FUSED_FFN and self._ffn is not None and self._ffn_ok(self.linear1, self.linear2, h):
+            # own kernels: gelu + dropout + operand split of the hidden tensor in one pass per direction
+            h = self._ffn(self.linear1, self.linear2, h, self.dropout.p, self.training)
+        else:
+            h = self.linear2(self.dropout(F.gelu(self.linear1(h))))
         return src + self.dropout2(h) * gate
 
 
