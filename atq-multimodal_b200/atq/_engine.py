@@ -616,6 +616,50 @@ def rpb_ffn(l1, l2, x, dropout_p: float = 0.0, training: bool = True, seed=None,
                            l2.weight, l2.alpha, l2.bias, l2.precision_mask, ops2, p, seed if p > 0.0 else None)
 
 
+class _GatedResidualFn(torch.autograd.Function):
+    """out = src + dropout(h) * g  (g: 1-element tensor, e.g. sigmoid(gate); models/text_encoder.py:238-249)."""
+
+    @staticmethod
+    def forward(ctx, src, h, g, p, seed):
+        src_c = nv.require_f32(src, "src")
+        h_c = nv.require_f32(h, "h")
+        g_c = nv.require_f32(g.detach().reshape(1), "gate")
+        dev = nv.device_index(src_c)
+        out = torch.empty_like(src_c)
+        nv.call("atq_gated_residual_fwd", dev, src_c.data_ptr(), h_c.data_ptr(), g_c.data_ptr(), src_c.numel(), float(p),
+                nv.ptr(seed), out.data_ptr(), nv.stream_ptr(dev))
+        ctx.save_for_backward(h_c, g_c)
+        ctx.seed, ctx.p, ctx.gshape = seed, float(p), g.shape
+        return out.view(src.shape)
+
+    @staticmethod
+    def backward(ctx, dout):
+        h_c, g_c = ctx.saved_tensors
+        d = nv.require_f32(dout, "grad_output")
+        dev = nv.device_index(d)
+        dh = torch.empty_like(h_c)
+        dg = torch.empty(1, dtype=torch.float32, device=d.device)
+        ws = nv.workspace(nv.lib.atq_workspace_bytes_gated_residual(d.numel()), d.device)
+        nv.call("atq_gated_residual_bwd", dev, d.data_ptr(), h_c.data_ptr(), g_c.data_ptr(), d.numel(), ctx.p, nv.ptr(ctx.seed),
+                dh.data_ptr(), dg.data_ptr(), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+        return dout, dh.view(dout.shape), dg.view(ctx.gshape), None, None
+
+
+def gated_residual_supported(src, h, g) -> bool:
+    return (src.is_cuda and src.dtype == torch.float32 and h.shape == src.shape and g.numel() == 1
+            and src.numel() > 0 and src.numel() % 4 == 0)
+
+
+def gated_residual(src, h, g, dropout_p: float = 0.0, training: bool = True, seed=None):
+    """src + dropout(h) * g in one pass (and one pass backward); the dropout mask is regenerated from a counter hash."""
+    if not gated_residual_supported(src, h, g):
+        raise RuntimeError("atq.gated_residual: needs fp32 CUDA tensors of equal shape (numel % 4 == 0) and a 1-element gate")
+    p = float(dropout_p) if training else 0.0
+    if p > 0.0 and seed is None:
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=src.device)
+    return _GatedResidualFn.apply(src, h, g, p, seed if p > 0.0 else None)
+
+
 def ternary_linear(x, weight, alpha, bias, cache: LayerOperands, sparsity_target=0.3, threshold_factor=0.05):
     ops = layer_operands(cache, weight, None, None, sparsity_target, threshold_factor)
     return _TernaryLinearFn.apply(x, weight, alpha, bias, ops)

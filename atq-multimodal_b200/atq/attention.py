@@ -128,16 +128,16 @@ def dropout_keep_mask(seed: int, batch: int, num_heads: int, seq_len: int, dropo
     return keep[:, :seq_len].reshape(batch, num_heads, seq_len, seq_len), thresh / 65536.0
 
 
-def dropout_keep_mask_flat(seed: int, numel: int, dropout_p: float):
-    """Host restatement of the fused-FFN dropout mask (csrc/streaming.cu:act_split_kernel): (keep bool [numel],
-    effective rate) over the flat row-major element index of the hidden tensor."""
+def dropout_keep_mask_flat(seed: int, numel: int, dropout_p: float, stream_id: int = 0x0FF1CE):
+    """Host restatement of the flat-index dropout masks of csrc/streaming.cu: (keep bool [numel], effective rate).
+    stream_id 0x0FF1CE = fused FFN activation (act_split_kernel), 0x6A7ED = gated residual."""
     import numpy as np
     if dropout_p <= 0:
         return np.ones(numel, dtype=bool), 0.0
     thresh = min(max(int(dropout_p * 65536.0 + 0.5), 1), 65535)
     seed_lo, seed_hi = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
     with np.errstate(over="ignore"):
-        x = (np.uint32(0x0FF1CE) * np.uint32(0x9E3779B1)) ^ seed_lo
+        x = (np.uint32(stream_id) * np.uint32(0x9E3779B1)) ^ seed_lo
         x ^= x >> np.uint32(16); x *= np.uint32(0x85EBCA6B); x ^= x >> np.uint32(13)
         key = x + seed_hi
         pair = np.arange((numel + 1) // 2, dtype=np.uint32)

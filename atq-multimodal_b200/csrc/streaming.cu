@@ -426,6 +426,85 @@ __global__ void __launch_bounds__(kThreads)
   if constexpr (BWD) *reinterpret_cast<float4*>(part + rl * cols + 4 * cg) = acc;
 }
 
+// ------------------------------------------------------------------------------------
+// Gated residual of the ternary transformer block (models/text_encoder.py:238-249):
+//   out = src + dropout(h) * g          g = sigmoid(gate), a device scalar
+// forward: one pass (read src, h; write out) instead of dropout + broadcast-multiply + add;
+// backward: dh = dout * g * keep/(1-p) and the per-CTA partials of dg = sum(dout .* dropout(h)) in one pass
+// over (dout, h); d(src) is dout itself.  The mask comes from the counter hash (seed, flat index).  n % 4 == 0.
+// ------------------------------------------------------------------------------------
+template <bool BWD>
+__global__ void __launch_bounds__(kThreads)
+    gated_residual_kernel(const float* __restrict__ a, const float* __restrict__ h, const float* __restrict__ g_p, int64_t n,
+                          float* __restrict__ out, float* __restrict__ part, const ActParams ap) {
+  const float gate = __ldg(g_p);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t key = 0;
+  if (ap.drop_thresh != 0u) {
+    const unsigned long long seed = ap.seed != nullptr ? *ap.seed : 0ull;
+    key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), 0x6A7EDu);
+  }
+  float acc = 0.f;
+  for (int64_t g0 = tid; g0 < n4; g0 += stride * kUnroll) {
+    float4 x[kUnroll], y[kUnroll];
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      const int64_t g = g0 + j * stride;
+      if (g < n4) { x[j] = ldg_stream4(a + 4 * g); y[j] = ldg_stream4(h + 4 * g); }
+    }
+#pragma unroll
+    for (int j = 0; j < kUnroll; ++j) {
+      const int64_t g = g0 + j * stride;
+      if (g >= n4) continue;
+      float k0 = 1.f, k1 = 1.f, k2 = 1.f, k3 = 1.f;
+      if (ap.drop_thresh != 0u) {
+        const uint32_t h0 = drop_hash_pair(key, (uint32_t)(2 * g)), h1 = drop_hash_pair(key, (uint32_t)(2 * g + 1));
+        k0 = (h0 & 0xFFFFu) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+        k1 = (h0 >> 16) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+        k2 = (h1 & 0xFFFFu) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+        k3 = (h1 >> 16) >= ap.drop_thresh ? ap.inv_keep : 0.f;
+      }
+      float4 o;
+      if constexpr (BWD) {  // a = dout
+        o = make_float4(x[j].x * gate * k0, x[j].y * gate * k1, x[j].z * gate * k2, x[j].w * gate * k3);
+        acc += (x[j].x * (y[j].x * k0) + x[j].y * (y[j].y * k1)) + (x[j].z * (y[j].z * k2) + x[j].w * (y[j].w * k3));
+      } else {              // a = src
+        o = make_float4(x[j].x + (y[j].x * k0) * gate, x[j].y + (y[j].y * k1) * gate, x[j].z + (y[j].z * k2) * gate,
+                        x[j].w + (y[j].w * k3) * gate);
+      }
+      *reinterpret_cast<float4*>(out + 4 * g) = o;
+    }
+  }
+  if constexpr (BWD) {
+    __shared__ float s_w[kThreads / 32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < kThreads / 32; ++i) t += s_w[i];
+      part[blockIdx.x] = t;
+    }
+  }
+}
+
+// fixed-order final sum of per-CTA partials (deterministic)
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int n, float* __restrict__ out) {
+  __shared__ double s[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += (double)part[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)s[0];
+}
+
 template <bool HAS_LO>
 __global__ void __launch_bounds__(kThreads)
     split_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
@@ -928,6 +1007,50 @@ int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y
   else act_split_kernel<true, false><<<grid, kThreads, 0, stream>>>(g, y, rows, cols, hi, lo, (float*)ws, R, ap);
   ATQ_LAUNCH_CHECK();
   colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>((const float*)ws, R, cols, colsum_out);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+size_t atq_workspace_bytes_gated_residual(int64_t n) {
+  (void)n;
+  return (size_t)4096 * sizeof(float);  // one partial per CTA, grid <= 4096
+}
+
+int atq_gated_residual_fwd(int device, const float* src, const float* h, const float* gate, int64_t n, float dropout_p,
+                           const unsigned long long* seed, float* out, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(src && h && gate && out && n > 0 && (n % 4) == 0, "null pointer or n not a positive multiple of 4");
+  ATQ_CHECK_ARG(aligned16(src) && aligned16(h) && aligned16(out), "16-byte aligned contiguous tensors");
+  ATQ_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && n < ((int64_t)1 << 33), "dropout_p in [0,1), n < 2^33");
+  ATQ_ENSURE_DEVICE(device);
+  ActParams ap;
+  dropout_threshold(dropout_p, &ap.drop_thresh, &ap.inv_keep);
+  ap.seed = seed;
+  int grid = stream_grid(device, n >> 2, kThreads * kUnroll, 8);
+  gated_residual_kernel<false><<<grid, kThreads, 0, (cudaStream_t)stream_>>>(src, h, gate, n, out, nullptr, ap);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_gated_residual_bwd(int device, const float* dout, const float* h, const float* gate, int64_t n, float dropout_p,
+                           const unsigned long long* seed, float* dh, float* dgate, void* ws, size_t ws_bytes,
+                           atq_stream_t stream_) {
+  ATQ_CHECK_ARG(dout && h && gate && dh && dgate && n > 0 && (n % 4) == 0, "null pointer or n not a positive multiple of 4");
+  ATQ_CHECK_ARG(aligned16(dout) && aligned16(h) && aligned16(dh), "16-byte aligned contiguous tensors");
+  ATQ_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f && n < ((int64_t)1 << 33), "dropout_p in [0,1), n < 2^33");
+  ATQ_ENSURE_DEVICE(device);
+  if (ws == nullptr || ws_bytes < atq_workspace_bytes_gated_residual(n)) {
+    set_error("atq_gated_residual_bwd: workspace too small");
+    return ATQ_EWORKSPACE;
+  }
+  ActParams ap;
+  dropout_threshold(dropout_p, &ap.drop_thresh, &ap.inv_keep);
+  ap.seed = seed;
+  int grid = stream_grid(device, n >> 2, kThreads * kUnroll, 8);
+  if (grid > 4096) grid = 4096;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  gated_residual_kernel<true><<<grid, kThreads, 0, stream>>>(dout, h, gate, n, dh, (float*)ws, ap);
+  ATQ_LAUNCH_CHECK();
+  sum_partials_kernel<<<1, 256, 0, stream>>>((const float*)ws, grid, dgate);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }

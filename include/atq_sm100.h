@@ -237,6 +237,16 @@ int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y
                                       const unsigned long long* seed, uint16_t* hi, uint16_t* lo, float* colsum_out,
                                       void* ws, size_t ws_bytes, atq_stream_t stream);
 
+/* Gated residual of the ternary transformer block (models/text_encoder.py:238-249):
+ *   out = src + dropout(h) * g   with g = sigmoid(gate) a device scalar; n % 4 == 0, contiguous tensors.
+ * backward: dh = dout * g * keep/(1-p), dgate = sum(dout .* dropout(h)) (deterministic two-stage sum); d(src) = dout. */
+size_t atq_workspace_bytes_gated_residual(int64_t n);
+int atq_gated_residual_fwd(int device, const float* src, const float* h, const float* gate, int64_t n, float dropout_p,
+                           const unsigned long long* seed, float* out, atq_stream_t stream);
+int atq_gated_residual_bwd(int device, const float* dout, const float* h, const float* gate, int64_t n, float dropout_p,
+                           const unsigned long long* seed, float* dh, float* dgate, void* ws, size_t ws_bytes,
+                           atq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,3 +78,31 @@ def test_fused_ffn_eval_mode_has_no_dropout_and_rejects_other_layers():
     assert not atq.fused_ffn_supported(t, l2, x)
     with pytest.raises(RuntimeError):
         atq.fused_ffn(t, l2, x)
+
+
+@pytest.mark.parametrize("shape,p", [((4, 50, 192), 0.0), ((4, 50, 192), 0.1), ((3, 197, 768), 0.1), ((7, 4), 0.5)])
+def test_gated_residual_matches_torch_sequence(shape, p):
+    g = torch.Generator(device=DEV).manual_seed(3)
+    src = torch.randn(*shape, device=DEV, generator=g)
+    h = torch.randn(*shape, device=DEV, generator=g)
+    gy = torch.randn(*shape, device=DEV, generator=g)
+    gate_param = torch.tensor([0.8], device=DEV)
+    seed_val = 99 + shape[-1]
+    seed = torch.tensor([seed_val], dtype=torch.int64, device=DEV)
+    keep, p_eff = A.dropout_keep_mask_flat(seed_val, src.numel(), p, stream_id=0x6A7ED)
+    keep = torch.from_numpy(keep).to(DEV).view(*shape).float()
+    outs = []
+    for fused in (True, False):
+        s_, h_, gp = src.clone().requires_grad_(True), h.clone().requires_grad_(True), gate_param.clone().requires_grad_(True)
+        gate = torch.sigmoid(gp)
+        if fused:
+            out = atq.gated_residual(s_, h_, gate, p, True, seed=seed)
+        else:
+            out = s_ + (h_ * keep / (1.0 - p_eff)) * gate
+        out.backward(gy)
+        outs.append((out.detach(), s_.grad, h_.grad, gp.grad))
+    for a, b in zip(*outs):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-5), (a - b).abs().max()
+    # eval mode: no dropout (the kernel contracts the multiply-add into one FMA, so compare with a tolerance)
+    assert torch.allclose(atq.gated_residual(src, h, torch.sigmoid(gate_param), 0.3, training=False),
+                          src + h * torch.sigmoid(gate_param), rtol=1e-6, atol=1e-6)

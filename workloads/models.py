@@ -117,6 +117,8 @@ class TernaryBlock(nn.Module):
         self.gate = nn.Parameter(torch.ones(1) * 0.8)
         self._ffn = getattr(layers, "fused_ffn", None)            # B200 package only
         self._ffn_ok = getattr(layers, "fused_ffn_supported", None)
+        self._gres = getattr(layers, "gated_residual", None)
+        self._gres_ok = getattr(layers, "gated_residual_supported", None)
 
     def update_sparsity(self, progress):
         s = self.initial_sparsity + progress * (self.target_sparsity - self.initial_sparsity)
@@ -129,14 +131,19 @@ class TernaryBlock(nn.Module):
         h = self.norm1(src)
         h = self.self_attn(h, h, h, key_padding_mask=key_padding_mask)
         gate = torch.sigmoid(self.gate)
-        src = src + self.dropout1(h) * gate
+        src = self._residual(src, h, gate, self.dropout1)
         h = self.norm2(src)
         if FUSED_FFN and self._ffn is not None and self._ffn_ok(self.linear1, self.linear2, h):
             # own kernels: gelu + dropout + operand split of the hidden tensor in one pass per direction
             h = self._ffn(self.linear1, self.linear2, h, self.dropout.p, self.training)
         else:
             h = self.linear2(self.dropout(F.gelu(self.linear1(h))))
-        return src + self.dropout2(h) * gate
+        return self._residual(src, h, gate, self.dropout2)
+
+    def _residual(self, src, h, gate, drop):
+        if FUSED_FFN and self._gres is not None and self._gres_ok(src, h, gate):
+            return self._gres(src, h, gate, drop.p, self.training)  # own kernel: one pass instead of three
+        return src + drop(h) * gate
 
 
 class TextEncoder(nn.Module):
