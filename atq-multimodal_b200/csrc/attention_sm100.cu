@@ -62,16 +62,31 @@ __device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w
 __device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // fp32 [rows_valid x 64] (row pitch in floats, 16-byte aligned rows) -> bf16 hi (+ lo) tiles of rows_total
-// swizzled 128-byte rows; rows >= rows_valid become zeros.  8 threads per row (32 B of fp32 each).
-template <bool LO>
+// swizzled 128-byte rows; rows >= rows_valid become zeros.  8 threads per row (32 B of fp32 each).  All global
+// loads of up to PASSES row passes (PASSES x 32 rows) are in flight before the first conversion, so a 128-row
+// tile (PASSES = 4) or a 256-row K / V tile (PASSES = 8) costs ONE memory round trip.
+__device__ __forceinline__ void convert_store_row(const float4& a, const float4& b, int r, int c, bool lo, uint32_t s_hi, uint32_t s_lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = pack2_bf16(x[2 * j], x[2 * j + 1]);
+    l[j] = pack2_bf16(x[2 * j] - bf16lo_f(h[j]), x[2 * j + 1] - bf16hi_f(h[j]));
+  }
+  const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4);
+  st_shared_v4(s_hi + off, make_uint4(h[0], h[1], h[2], h[3]));
+  if (lo) st_shared_v4(s_lo + off, make_uint4(l[0], l[1], l[2], l[3]));
+}
+
+template <bool LO, int PASSES = 4>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t pitch, int rows_valid, int rows_total,
                                            uint32_t s_hi, uint32_t s_lo) {
   const int c = threadIdx.x & 7;
   constexpr int kRowsPerPass = kAttThreads / 8;  // 32
-  for (int r0 = threadIdx.x >> 3; r0 < rows_total; r0 += 4 * kRowsPerPass) {
-    float4 a[4], b[4];
+  for (int r0 = threadIdx.x >> 3; r0 < rows_total; r0 += PASSES * kRowsPerPass) {
+    float4 a[PASSES], b[PASSES];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // all loads of four passes in flight before the first conversion
+    for (int i = 0; i < PASSES; ++i) {
       const int r = r0 + i * kRowsPerPass;
       if (r < rows_valid) {
         const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * pitch + 8 * c);
@@ -83,21 +98,37 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < PASSES; ++i) {
       const int r = r0 + i * kRowsPerPass;
-      if (r < rows_total) {
-        const float x[8] = {a[i].x, a[i].y, a[i].z, a[i].w, b[i].x, b[i].y, b[i].z, b[i].w};
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          h[j] = pack2_bf16(x[2 * j], x[2 * j + 1]);
-          if (LO) l[j] = pack2_bf16(x[2 * j] - bf16lo_f(h[j]), x[2 * j + 1] - bf16hi_f(h[j]));
-        }
-        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4);
-        st_shared_v4(s_hi + off, make_uint4(h[0], h[1], h[2], h[3]));
-        if (LO) st_shared_v4(s_lo + off, make_uint4(l[0], l[1], l[2], l[3]));
-      }
+      if (r < rows_total) convert_store_row(a[i], b[i], r, c, LO, s_hi, s_lo);
     }
+  }
+}
+
+// two 128-row tiles (e.g. Q and dO) with the loads of both in flight together
+template <bool LO>
+__device__ __forceinline__ void stage_two_tiles(const float* __restrict__ src0, int64_t pitch0, uint32_t s_hi0, uint32_t s_lo0,
+                                                const float* __restrict__ src1, int64_t pitch1, uint32_t s_hi1, uint32_t s_lo1,
+                                                int rows_valid) {
+  const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+  float4 a0[4], b0[4], a1[4], b1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + i * 32;
+    if (r < rows_valid) {
+      const float4* p0 = reinterpret_cast<const float4*>(src0 + (int64_t)r * pitch0 + 8 * c);
+      const float4* p1 = reinterpret_cast<const float4*>(src1 + (int64_t)r * pitch1 + 8 * c);
+      a0[i] = __ldg(p0); b0[i] = __ldg(p0 + 1);
+      a1[i] = __ldg(p1); b1[i] = __ldg(p1 + 1);
+    } else {
+      a0[i] = b0[i] = a1[i] = b1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + i * 32;
+    convert_store_row(a0[i], b0[i], r, c, LO, s_hi0, s_lo0);
+    convert_store_row(a1[i], b1[i], r, c, LO, s_hi1, s_lo1);
   }
 }
 
@@ -193,11 +224,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   const float* kg = p.k + (int64_t)b * L * p.k_pitch + h * kHd;
   const float* vg = p.v + (int64_t)b * L * p.v_pitch + h * kHd;
   if (lo) {
-    stage_tile<true>(kg, p.k_pitch, L, NK, s_kh, s_kl);
-    stage_tile<true>(vg, p.v_pitch, L, NK, s_vh, s_vl);
+    stage_tile<true, 8>(kg, p.k_pitch, L, NK, s_kh, s_kl);
+    stage_tile<true, 8>(vg, p.v_pitch, L, NK, s_vh, s_vl);
   } else {
-    stage_tile<false>(kg, p.k_pitch, L, NK, s_kh, 0);
-    stage_tile<false>(vg, p.v_pitch, L, NK, s_vh, 0);
+    stage_tile<false, 8>(kg, p.k_pitch, L, NK, s_kh, 0);
+    stage_tile<false, 8>(vg, p.v_pitch, L, NK, s_vh, 0);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -300,6 +331,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       const int vterms = lo ? 2 : 1;
       for (int term = 0; term < vterms; ++term) {  // P_hi V_hi, P_hi V_lo
         const uint32_t sb = term == 1 ? s_vl : s_vh;
+#pragma unroll 2
         for (int j = 0; j < NK / UMMA_K; ++j) {
           const uint64_t da = make_smem_desc_kmajor_sw128(s_p + (uint32_t)(j >> 2) * (uint32_t)kTileBytes + (uint32_t)(j & 3) * 32u);
           const uint64_t db = make_smem_desc_mnmajor_sw128(sb + (uint32_t)j * 2048u, 8192);
@@ -404,37 +436,32 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
     const int k_valid = (L - k0) < 128 ? (L - k0) : 128;
     const float* kg = p.k + ((int64_t)b * L + k0) * p.k_pitch + h * kHd;
     const float* vg = p.v + ((int64_t)b * L + k0) * p.v_pitch + h * kHd;
-    if (lo) {
-      stage_tile<true>(kg, p.k_pitch, k_valid, 128, s_kh, s_kl);
-      stage_tile<true>(vg, p.v_pitch, k_valid, 128, s_vh, s_vl);
-    } else {
-      stage_tile<false>(kg, p.k_pitch, k_valid, 128, s_kh, 0);
-      stage_tile<false>(vg, p.v_pitch, k_valid, 128, s_vh, 0);
-    }
+    if (lo) stage_two_tiles<true>(kg, p.k_pitch, s_kh, s_kl, vg, p.v_pitch, s_vh, s_vl, k_valid);
+    else stage_two_tiles<false>(kg, p.k_pitch, s_kh, 0, vg, p.v_pitch, s_vh, 0, k_valid);
     for (int q0 = 0; q0 < L; q0 += 128) {
       const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
       const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * kHd;
       const float* dg = p.dout + ((int64_t)b * L + q0) * p.do_pitch + h * kHd;
-      if (lo) {
-        stage_tile<true>(qg, p.q_pitch, q_valid, 128, s_qh, s_ql);
-        stage_tile<true>(dg, p.do_pitch, q_valid, 128, s_dh, s_dl);
-      } else {
-        stage_tile<false>(qg, p.q_pitch, q_valid, 128, s_qh, 0);
-        stage_tile<false>(dg, p.do_pitch, q_valid, 128, s_dh, 0);
-      }
-      // delta = sum_d dO[q,d] * O[q,d] over this head (row-sum of P .* dP): each column half adds 32 columns
+      // delta = sum_d dO[q,d] * O[q,d] over this head (row-sum of P .* dP): each column half adds 32 columns.
+      // Its loads are issued before the tile staging so that their latency hides behind the conversions.
       const int q = q0 + row;
       const bool q_ok = q < L;
+      float4 dx[8], dy[8];
+      if (q_ok) {
+        const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * kHd + half * 32);
+        const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * kHd + half * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dx[j] = __ldg(po + j); dy[j] = __ldg(pd + j); }
+      }
+      const float lse_q = q_ok ? __ldg(p.lse + (int64_t)bh * L + q) : 0.f;
+      if (lo) stage_two_tiles<true>(qg, p.q_pitch, s_qh, s_ql, dg, p.do_pitch, s_dh, s_dl, q_valid);
+      else stage_two_tiles<false>(qg, p.q_pitch, s_qh, 0, dg, p.do_pitch, s_dh, 0, q_valid);
       {
         float d = 0.f;
         if (q_ok) {
-          const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * kHd + half * 32);
-          const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * kHd + half * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = __ldg(po + j), y = __ldg(pd + j);
-            d += (x.x * y.x + x.y * y.y) + (x.z * y.z + x.w * y.w);
-          }
+          for (int j = 0; j < 8; ++j)
+            d += (dx[j].x * dy[j].x + dx[j].y * dy[j].y) + (dx[j].z * dy[j].z + dx[j].w * dy[j].w);
         }
         s_red[half][row] = d;
       }
@@ -461,7 +488,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         umma_commit(bar);
       }
       const float delta = s_red[0][row] + s_red[1][row];
-      const float lse2 = q_ok ? p.lse[(int64_t)bh * L + q] * 1.4426950408889634f : 0.f;
+      const float lse2 = lse_q * 1.4426950408889634f;
       const uint32_t row_key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * L + q));
       mbar_wait(bar, phase);
       phase ^= 1u;
@@ -518,6 +545,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         uint32_t acc = 0;
         for (int term = 0; term < p.terms; ++term) {
           const uint32_t sa = term == 1 ? s_dsl : s_ds, sb = term == 2 ? s_kl : s_kh;
+#pragma unroll
           for (int j = 0; j < 128 / UMMA_K; ++j) {
             const uint64_t da = make_smem_desc_kmajor_sw128(sa + (uint32_t)(j >> 2) * T + (uint32_t)(j & 3) * 32u);
             const uint64_t db = make_smem_desc_mnmajor_sw128(sb + (uint32_t)j * 2048u, 8192);
@@ -533,7 +561,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
           for (int term = 0; term < nterm; ++term) {
             const uint32_t sa = which ? s_p : (term == 1 ? s_dsl : s_ds);
             const uint32_t sb = which ? (term ? s_dl : s_dh) : (term == 2 ? s_ql : s_qh);
-            for (int j = 0; j < 128 / UMMA_K; ++j) {
+  #pragma unroll
+          for (int j = 0; j < 128 / UMMA_K; ++j) {
               const uint64_t da = make_smem_desc_mnmajor_sw128(sa + (uint32_t)j * 2048u, T);
               const uint64_t db = make_smem_desc_mnmajor_sw128(sb + (uint32_t)j * 2048u, 8192);
               umma_bf16(td, da, db, idesc_t, acc2);
@@ -577,6 +606,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         if (threadIdx.x == 0) {
           tcgen05_fence_after();
           const uint32_t idesc_t = make_idesc_rt(kHd, true, true);
+#pragma unroll
           for (int j = 0; j < 128 / UMMA_K; ++j) {
             const uint64_t da = make_smem_desc_mnmajor_sw128(s_p + (uint32_t)j * 2048u, T);
             const uint64_t db = make_smem_desc_mnmajor_sw128(s_dh + (uint32_t)j * 2048u, 8192);
