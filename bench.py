@@ -358,7 +358,8 @@ def run_ours(args, cfg):
     # the small-shape config is launch-bound and runs as one CUDA graph; the ViT-B-sized config is
     # kernel-bound (and its activations would be held twice by a capture pool), so it runs eagerly
     use_graph = (not args.no_graph) and args.workload == "flickr8k"
-    opt = T.make_optimizer(model, cfg, capturable=use_graph, fused=True)
+    from atq.optim import FlatAdamW
+    opt = T.make_optimizer(model, cfg, capturable=use_graph, fused=True, adamw_cls=None if args.torch_adamw else FlatAdamW)
     sync = None
     if world > 1:  # --sparse-grads: only the entries under each RPB precision_mask travel
         sync = parallel.FlatGradAllReduce(model.parameters(), sparse_masks=parallel.rpb_masks(model) if args.sparse_grads else None)
@@ -501,6 +502,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of atq.optim.FlatAdamW")
     ap.add_argument("--sparse-grads", action="store_true", help="N>1: all-reduce only the masked entries of RPB weight gradients")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

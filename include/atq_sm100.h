@@ -247,6 +247,14 @@ int atq_gated_residual_bwd(int device, const float* dout, const float* h, const 
                            const unsigned long long* seed, float* dh, float* dgate, void* ws, size_t ws_bytes,
                            atq_stream_t stream);
 
+/* AdamW over a table of tensors in one launch (the optimizer step of train_multimodal.py:361-366; same update
+ * as torch.optim.AdamW, no amsgrad).  table: device array of {float* p; const float* g; float* m; float* v;
+ * int64 n} (16-byte aligned pointers, the four tensors of an entry share one memory layout); work unit c =
+ * elements [1024*chunk_off[c], +1024) of tensor chunk_tensor[c].  step: device scalar holding the number of
+ * completed steps (bias correction uses step+1; the call increments it - CUDA-graph replays advance it). */
+int atq_adamw_multi(int device, const void* table, const int* chunk_tensor, const int* chunk_off, int n_chunks, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, float* step, atq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,9 +58,11 @@ def build_retrieval(layers, cfg: RetrievalCfg, seed=42):
     return model, criterion, manager
 
 
-def make_optimizer(model, cfg: RetrievalCfg, capturable=False, fused=False):
+def make_optimizer(model, cfg: RetrievalCfg, capturable=False, fused=False, adamw_cls=None):
     # train_multimodal.py:361-366 (AdamW, betas (0.9, 0.98)); `fused` only selects torch's single-kernel
-    # CUDA implementation of the same update
+    # CUDA implementation of the same update; `adamw_cls` (atq.optim.FlatAdamW) the one-launch own kernel
+    if adamw_cls is not None:
+        return adamw_cls(model.parameters(), lr=cfg.lr, weight_decay=1e-4, betas=(0.9, 0.98))
     kw = dict(fused=True) if fused else {}
     return torch.optim.AdamW(model.parameters(), lr=cfg.lr, weight_decay=1e-4, betas=(0.9, 0.98),
                              capturable=capturable, **kw)
