@@ -86,7 +86,9 @@ class FlatGradAllReduce:
             self.sparse_idx.append(torch.nonzero(mask.reshape(-1) != 0).reshape(-1) if ok else None)
         self._mask_versions = self._versions()
         sizes = [p.numel() if idx is None else idx.numel() for p, idx in zip(self.active, self.sparse_idx)]
-        self.flat = torch.empty(sum(sizes), dtype=torch.float32, device=self.active[0].device)
+        # every slice starts on a 16-byte boundary (vectorised consumers such as atq.optim.FlatAdamW); the padding
+        # elements stay zero and simply travel with the all-reduce
+        self.flat = torch.zeros(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=self.active[0].device)
         self.views = []
         off = 0
         for p, idx, n in zip(self.active, self.sparse_idx, sizes):
@@ -98,7 +100,7 @@ class FlatGradAllReduce:
                 # fused optimizers require param/grad layouts to match); dense tensors only
                 dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
                 self.views.append(piece.as_strided(p.size(), p.stride()) if dense else piece.view_as(p))
-            off += n
+            off += (n + 3) // 4 * 4
 
     def zero_grad(self):
         """Drop every gradient so autograd writes fresh tensors (no read-modify-write accumulation)."""

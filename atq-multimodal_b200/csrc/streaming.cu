@@ -533,7 +533,10 @@ __global__ void __launch_bounds__(256)
     const AdamwTensor T = table[chunk_tensor[c]];
     const long long base = (long long)chunk_off[c] * kAdamChunk;
     const long long i = base + 4 * (long long)threadIdx.x;
-    if (i + 3 < T.n) {
+    // 128-bit path only when all four tensors are 16-byte aligned (gradient views into a flat all-reduce buffer may not be)
+    const bool vec = ((reinterpret_cast<uintptr_t>(T.p) | reinterpret_cast<uintptr_t>(T.g) | reinterpret_cast<uintptr_t>(T.m) |
+                       reinterpret_cast<uintptr_t>(T.v)) & 15u) == 0;
+    if (vec && i + 3 < T.n) {
       const float4 g = *reinterpret_cast<const float4*>(T.g + i);
       float4 p = *reinterpret_cast<const float4*>(T.p + i);
       float4 m = *reinterpret_cast<const float4*>(T.m + i);

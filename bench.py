@@ -348,6 +348,9 @@ def run_ours(args, cfg):
     atq.set_gemm_mode(args.mode)
     peaks = load_peaks()
 
+    if args.serial_towers:
+        from workloads import models as WM
+        WM.PARALLEL_TOWERS = False
     model, _, manager = T.build_retrieval(atq, cfg)
     model.to(device).train()
     if cfg.image_tower == "resnet18":
@@ -426,7 +429,9 @@ def run_ours(args, cfg):
                        "gemm_arithmetic": "bf16 hi+lo operand pairs, fp32 TMEM accumulate" if args.mode == "parity"
                        else "bf16 operands, fp32 TMEM accumulate",
                        "quant_schedule": f"GradualQuantizationScheduler epoch {cfg.epoch}/{cfg.total_epochs}",
-                       "execution": "whole step captured in one CUDA graph" if use_graph else "eager",
+                       "execution": ("whole step captured in one CUDA graph" + ("" if args.serial_towers or cfg.image_tower != "resnet18" else
+                                                                                 ", image / text towers on two streams (concurrent graph branches)"))
+                       if use_graph else "eager",
                        "l2": "flushed between timed steps (256 MB write, outside the per-step events)"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / args.steps, 4)},
@@ -502,6 +507,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--serial-towers", action="store_true", help="run the image and text towers on one stream (no graph branch concurrency)")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of atq.optim.FlatAdamW")
     ap.add_argument("--sparse-grads", action="store_true", help="N>1: all-reduce only the masked entries of RPB weight gradients")
     args = ap.parse_args()

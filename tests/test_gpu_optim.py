@@ -66,3 +66,17 @@ def test_flat_adamw_cuda_graph_replays_advance_the_step_counter():
         ob.step()
     for (n, pa), pb in zip(a.named_parameters(), b.parameters()):
         assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), (n, (pa - pb).abs().max().item())
+
+
+def test_flat_adamw_accepts_unaligned_gradient_views():
+    """p.grad as a view into a flat buffer at an odd element offset (what a flat gradient all-reduce produces)."""
+    torch.manual_seed(3)
+    pa = nn.Parameter(torch.randn(1000, device=DEV))
+    pb = nn.Parameter(pa.detach().clone())
+    flat = torch.randn(1003, device=DEV)
+    pa.grad = flat[3:]            # 12-byte offset
+    pb.grad = flat[3:].clone()
+    oa, ob = FlatAdamW([pa], **HP), torch.optim.AdamW([pb], **HP)
+    for _ in range(3):
+        oa.step(); ob.step()
+    assert torch.allclose(pa, pb, rtol=1e-5, atol=1e-6)

@@ -108,7 +108,8 @@ def _sparse_worker(rank, world, port, out_dir):
         results[kind] = [p.grad.clone() for p in params if p.grad is not None]
         results[kind + "_flat"] = sync.flat.numel()
     nnz = int((enc.precision_mask != 0).sum())
-    assert results["dense_flat"] - results["sparse_flat"] == enc.weight.numel() - nnz
+    pad4 = lambda n: (n + 3) // 4 * 4  # slices are padded to 16 bytes
+    assert results["dense_flat"] - results["sparse_flat"] == pad4(enc.weight.numel()) - pad4(nnz)
     for a, b in zip(results["dense"], results["sparse"]):
         assert torch.equal(a, b)
     wg = results["sparse"][0]

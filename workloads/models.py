@@ -30,6 +30,8 @@ def _lengths_to_mask(lengths, batch, seq, device):
 FUSED_ATTENTION_CORE = True
 # True: linear2(dropout(gelu(linear1(h)))) of a TernaryBlock runs through atq.fused_ffn when both layers are RPB
 FUSED_FFN = True
+# True: RetrievalModel instances with `parallel_towers = True` run the text tower on a side stream
+PARALLEL_TOWERS = True
 
 
 class TernaryAttention(nn.Module):
@@ -300,6 +302,8 @@ class RetrievalModel(nn.Module):
                  max_seq_length=50, vit_cfg=None):
         super().__init__()
         self.use_rpb, self.embed_dim = use_residual, embed_dim
+        self.parallel_towers = image_tower == "resnet18"  # small-shape (launch-bound) config only
+        self._side = None
         self.initial_vision_sparsity = min(0.1, vision_threshold)
         self.initial_text_sparsity = min(0.1, text_threshold)
         self.target_vision_sparsity, self.target_text_sparsity = vision_threshold, text_threshold
@@ -344,6 +348,20 @@ class RetrievalModel(nn.Module):
 
     def forward(self, image, text, text_lengths=None, return_embeddings=True):
         assert return_embeddings, "only the training path of the reference is re-created"
+        if PARALLEL_TOWERS and image.is_cuda and self.parallel_towers:
+            # The two towers are independent until the loss: run the text tower on a side stream.  In the
+            # launch-bound small-shape config the towers' kernels use a handful of SMs each, so the branches of the
+            # captured CUDA graph (forward and, through autograd's per-node streams, backward) run concurrently.
+            cur = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                txt = self.encode_text(text, text_lengths)
+            img = self.encode_image(image)
+            cur.wait_stream(self._side)
+            txt.record_stream(cur)
+            return img, txt
         return self.encode_image(image), self.encode_text(text, text_lengths)
 
 
