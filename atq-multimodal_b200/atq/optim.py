@@ -9,7 +9,6 @@ counter lives on the device and the pointer table is uploaded from pinned host m
 """
 from __future__ import annotations
 
-import ctypes
 import struct
 
 import torch
