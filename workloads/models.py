@@ -304,6 +304,7 @@ class RetrievalModel(nn.Module):
         self.use_rpb, self.embed_dim = use_residual, embed_dim
         self.parallel_towers = image_tower == "resnet18"  # small-shape (launch-bound) config only
         self._side = None
+        self.prepare_fn = None  # optional: atq.prepare_quantization, called per tower inside forward
         self.initial_vision_sparsity = min(0.1, vision_threshold)
         self.initial_text_sparsity = min(0.1, text_threshold)
         self.target_vision_sparsity, self.target_text_sparsity = vision_threshold, text_threshold
@@ -357,11 +358,18 @@ class RetrievalModel(nn.Module):
                 self._side = torch.cuda.Stream()
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
+                if self.prepare_fn is not None:  # batched re-quantization of this tower's layers, on its own branch
+                    self.prepare_fn(self.text_encoder)
+                    self.prepare_fn(self.text_projector)
                 txt = self.encode_text(text, text_lengths)
+            if self.prepare_fn is not None:
+                self.prepare_fn(self.image_encoder)
             img = self.encode_image(image)
             cur.wait_stream(self._side)
             txt.record_stream(cur)
             return img, txt
+        if self.prepare_fn is not None:
+            self.prepare_fn(self)
         return self.encode_image(image), self.encode_text(text, text_lengths)
 
 

@@ -90,7 +90,10 @@ def retrieval_step(model, manager, optimizer, batch, gather=None, grad_sync=None
     else:
         optimizer.zero_grad(set_to_none=True)
     if prepare is not None:
-        prepare(model)  # batched re-quantization of every layer the last optimizer step touched
+        if getattr(model, "parallel_towers", False) and images.is_cuda:
+            model.prepare_fn = prepare  # each tower re-quantizes its own layers on its own stream (models.py)
+        else:
+            prepare(model)  # batched re-quantization of every layer the last optimizer step touched
     img, txt = model(images, captions, lengths, return_embeddings=True)
     if gather is not None:
         img, txt = gather(img), gather(txt)
