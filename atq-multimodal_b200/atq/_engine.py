@@ -8,9 +8,14 @@ gradient contract:
 with G = dY^T X.  A true straight-through estimator (dW = G for TernaryLinear) is opt-in
 (`atq.set_ste(True)`), off by default, and never used by the parity tests.
 
-GEMM precision modes: "parity" (default) feeds every fp32 operand as a bf16 hi+lo
-pair (2-3 tcgen05.mma terms into one TMEM accumulator; matches the fp32 reference within
-rtol 1e-2 / atol 1e-3); "fast" uses the hi term only.
+GEMM precision modes (every mode accumulates in fp32 in TMEM):
+  "parity" (default)  every fp32 operand travels as a SCALED fp16 (hi, lo) pair: one power-of-two scale per tensor
+                      (max|s x| in [2^14, 2^15), found by a grid-level |x| max reduction), hi = fp16(s x),
+                      lo = fp16(s x - hi), 2-3 tcgen05.mma terms into one accumulator, 1/s applied in the epilogue.
+                      ~22 significant bits per operand: the reference's own models keep fp32-level gradients on it.
+  "parity_bf16"       the same terms on bf16 (hi, lo) pairs, no scale pass (~16 bits; meets rtol 1e-2 / atol 1e-3 on a
+                      single layer, but a deep, badly conditioned network amplifies its 2^-17 to per-cent level)
+  "fast"              one bf16 term.
 """
 from __future__ import annotations
 
@@ -34,8 +39,8 @@ _PACKED_AUTO_MAX_TOKENS = 256
 
 def set_gemm_mode(mode: str) -> None:
     global _MODE
-    if mode not in ("parity", "fast"):
-        raise ValueError("mode must be 'parity' or 'fast'")
+    if mode not in ("parity", "parity_bf16", "fast"):
+        raise ValueError("mode must be 'parity', 'parity_bf16' or 'fast'")
     _MODE = mode
 
 
@@ -49,6 +54,10 @@ def set_ste(enabled: bool) -> None:
 
 
 def _use_lo() -> bool:
+    return _MODE != "fast"
+
+
+def _use_f16() -> bool:
     return _MODE == "parity"
 
 
@@ -185,32 +194,65 @@ def route_mask_mul(x: torch.Tensor, grad_out: torch.Tensor, thr: torch.Tensor) -
     return out
 
 
-def split_bf16(x2: torch.Tensor, want_lo: bool):
-    """fp32 [rows, cols] -> (hi, lo|None, pitch) bf16 row-major."""
+def absmax_slot(x2: torch.Tensor, bound_mul: float = 1.0, extra: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Scale slot of a scaled-fp16 operand: one grid-level max|x| reduction; slot[1] = s, slot[2] = 1/s with
+    max(max|x|, |extra|) * bound_mul * s in [2^14, 2^15).  No host synchronisation."""
+    rows, cols = x2.shape
+    dev = nv.device_index(x2)
+    slot = nv.new_slot(x2.device)
+    nv.call("atq_absmax_scale", dev, x2.data_ptr(), rows, cols, x2.stride(0), float(bound_mul), nv.ptr(extra),
+            slot.data_ptr(), nv.stream_ptr(dev))
+    return slot
+
+
+def split_bf16(x2: torch.Tensor, want_lo: bool, slot: Optional[torch.Tensor] = None):
+    """fp32 [rows, cols] -> (hi, lo|None, pitch) row-major: bf16 pair, or (when a scale slot is given) the scaled
+    fp16 pair as (hi, lo, pitch, 0, slot)."""
     rows, cols = x2.shape
     dev = nv.device_index(x2)
     pitch = nv.round_up(cols, 8)
-    hi = torch.empty((rows, pitch), dtype=torch.bfloat16, device=x2.device)
-    lo = torch.empty((rows, pitch), dtype=torch.bfloat16, device=x2.device) if want_lo else None
+    dt = torch.bfloat16 if slot is None else torch.float16
+    hi = torch.empty((rows, pitch), dtype=dt, device=x2.device)
+    lo = torch.empty((rows, pitch), dtype=dt, device=x2.device) if want_lo else None
     nv.call("atq_split_bf16", dev, x2.data_ptr(), rows, cols, x2.stride(0), hi.data_ptr(), nv.ptr(lo), pitch,
-            nv.stream_ptr(dev))
-    return hi, lo, pitch
+            nv.ptr(slot), nv.stream_ptr(dev))
+    return (hi, lo, pitch) if slot is None else (hi, lo, pitch, 0, slot)
 
 
-def split_bf16_colsum(x2: torch.Tensor, want_lo: bool):
+def split_operand(x2: torch.Tensor):
+    """The A operand of a GEMM in the current precision mode (see the module docstring)."""
+    if _use_f16():
+        return split_bf16(x2, True, absmax_slot(x2))
+    hi, lo, pitch = split_bf16(x2, _use_lo())
+    return (hi, lo, pitch, 0, None)
+
+
+def mn_view(op):
+    """The same operand memory consumed MN-major ([k, rows] row-major view of a row-major tensor)."""
+    return (op[0], op[1], op[2], 1, op[4] if len(op) > 4 else None)
+
+
+def split_bf16_colsum(x2: torch.Tensor, want_lo: bool, slot: Optional[torch.Tensor] = None):
     """split_bf16 of a contiguous [rows, cols] tensor fused with its column sums (bias gradient).
     Falls back to the two separate kernels when the fused path's layout conditions do not hold."""
     rows, cols = x2.shape
     if cols % 8 != 0 or x2.stride(0) != cols or x2.data_ptr() % 16 != 0:
-        return split_bf16(x2, want_lo), colsum(x2)
+        op = split_bf16(x2, want_lo, slot)
+        return (op + (0, None) if len(op) == 3 else op), colsum(x2)
     dev = nv.device_index(x2)
-    hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=x2.device)
-    lo = torch.empty((rows, cols), dtype=torch.bfloat16, device=x2.device) if want_lo else None
+    dt = torch.bfloat16 if slot is None else torch.float16
+    hi = torch.empty((rows, cols), dtype=dt, device=x2.device)
+    lo = torch.empty((rows, cols), dtype=dt, device=x2.device) if want_lo else None
     out = torch.empty(cols, dtype=torch.float32, device=x2.device)
     ws = nv.workspace(nv.lib.atq_workspace_bytes_split_colsum(rows, cols), x2.device)
     nv.call("atq_split_bf16_colsum", dev, x2.data_ptr(), rows, cols, hi.data_ptr(), nv.ptr(lo), out.data_ptr(),
-            ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
-    return (hi, lo, cols), out
+            ws.data_ptr(), ws.numel(), nv.ptr(slot), nv.stream_ptr(dev))
+    return (hi, lo, cols, 0, slot), out
+
+
+def split_operand_colsum(x2: torch.Tensor, want_lo: bool, f16: bool):
+    """Operand split + column sums with the format of the OTHER operand of the GEMMs it feeds (saved from forward)."""
+    return split_bf16_colsum(x2, want_lo, absmax_slot(x2) if f16 else None)
 
 
 def split_bf16_t(x2: torch.Tensor, want_lo: bool):
@@ -221,7 +263,7 @@ def split_bf16_t(x2: torch.Tensor, want_lo: bool):
     hi = torch.empty((cols, pitch_t), dtype=torch.bfloat16, device=x2.device)
     lo = torch.empty((cols, pitch_t), dtype=torch.bfloat16, device=x2.device) if want_lo else None
     nv.call("atq_split_bf16_t", dev, x2.data_ptr(), rows, cols, x2.stride(0), hi.data_ptr(), nv.ptr(lo), pitch_t,
-            None, nv.stream_ptr(dev))
+            None, None, nv.stream_ptr(dev))
     return hi, lo, pitch_t
 
 
@@ -344,21 +386,25 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
         thr = adaptive_threshold(w, sparsity_target, threshold_factor)
     pitch, pitch_t = nv.round_up(K, 8), nv.round_up(M, 8)
     n = M * K
-    bf = torch.bfloat16
     packed = torch.empty((n + 3) // 4, dtype=torch.uint8, device=w.device)
     flat_ok = (K % 4 == 0)
     st = nv.stream_ptr(dev)
     packed_t = None
+    f16 = _use_f16()
+    bf = torch.float16 if f16 else torch.bfloat16
+    slot = None
     if mask is None:
         # TernaryLinear: the GEMMs read the 2-bit codec bytes directly whenever the contraction
-        # dimension allows 16-byte codec rows per k-block; bf16 copies only for odd shapes
+        # dimension allows 16-byte codec rows per k-block; 16-bit copies only for odd shapes.  T is exact in
+        # bf16 and in fp16 (no scale): the copy just has to carry the element format of the activations.
         hi = torch.empty((M, pitch), dtype=bf, device=w.device)
         hi_t = None  # dX reads `hi` in place through MN-major descriptors
         if M % 64 == 0:
             packed_t = torch.empty(n // 4, dtype=torch.uint8, device=w.device)
         lo = lo_t = None
         nv.call("atq_build_ternary_operands", dev, w.data_ptr(), M, K, thr.data_ptr(),
-                packed.data_ptr() if flat_ok else None, nv.ptr(packed_t), nv.ptr(hi), pitch, nv.ptr(hi_t), pitch_t, None, st)
+                packed.data_ptr() if flat_ok else None, nv.ptr(packed_t), nv.ptr(hi), pitch, nv.ptr(hi_t), pitch_t, None,
+                1 if f16 else 0, st)
     else:
         want_lo = _use_lo()
         hi = torch.empty((M, pitch), dtype=bf, device=w.device)
@@ -366,13 +412,16 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
         hi_t = lo_t = None  # dX reads hi/lo in place through MN-major descriptors
         mk = nv.require_f32(mask, "precision_mask")
         al = nv.require_f32(alpha.detach(), "alpha")
+        if f16:  # |Wm| <= max(max|W|, |alpha|): one reduction over W gives the scale of the mixed operand
+            slot = absmax_slot(w, 1.0, al)
         nv.call("atq_build_mixed_operands", dev, w.data_ptr(), mk.data_ptr(), M, K, thr.data_ptr(), al.data_ptr(),
-                packed.data_ptr() if flat_ok else None, hi.data_ptr(), nv.ptr(lo), pitch, None, None, pitch_t, st)
+                packed.data_ptr() if flat_ok else None, hi.data_ptr(), nv.ptr(lo), pitch, None, None, pitch_t,
+                nv.ptr(slot), st)
     if not flat_ok:  # rows of the flat codec do not start on byte boundaries
         nv.call("atq_ternarize_pack2", dev, w.data_ptr(), n, thr.data_ptr(), packed.data_ptr(), None, st)
     cache.key, cache.thr, cache.packed, cache.packed_t = key, thr, packed, packed_t
-    cache.w = (hi, lo, pitch)           # [M, pitch]: forward B operand (K-major) ...
-    cache.w_t = (hi, lo, pitch, 1)      # ... and, read as MN-major, the dX B operand (no transposed copy)
+    cache.w = (hi, lo, pitch, 0, slot)     # [M, pitch]: forward B operand (K-major) ...
+    cache.w_t = (hi, lo, pitch, 1, slot)   # ... and, read as MN-major, the dX B operand (no transposed copy)
     return cache
 
 
@@ -418,7 +467,7 @@ class _TernaryLinearFn(torch.autograd.Function):
         if N == 0:
             y = x2.new_zeros((0, M))
         else:
-            xa = split_bf16(x2, _use_lo())
+            xa = split_operand(x2)
             b_ = None if bias is None else bias.detach()
             if _want_packed(N) and packed_gemm_ok(K, ops.packed):
                 # packed 2-bit weights, expanded to bf16 tiles inside the GEMM
@@ -431,6 +480,7 @@ class _TernaryLinearFn(torch.autograd.Function):
         ctx.wshape = (M, K)
         ctx.xshape = x.shape
         ctx.ste = _STE
+        ctx.fmt = (_use_lo(), _use_f16())  # backward uses the element format the cached weight operand was built in
         return y.reshape(*x.shape[:-1], M)
 
     @staticmethod
@@ -443,10 +493,11 @@ class _TernaryLinearFn(torch.autograd.Function):
             g2 = g2.contiguous()
         if N == 0:
             return (gy.new_zeros(ctx.xshape), None, al.new_zeros(1), g2.new_zeros(M) if ctx.has_bias else None, None)
+        want_lo, f16 = ctx.fmt
         if ctx.has_bias:
-            ga, dbias = split_bf16_colsum(g2, _use_lo())  # one pass over dY: operand split + bias gradient
+            ga, dbias = split_operand_colsum(g2, want_lo, f16)  # one pass over dY: operand split + bias gradient
         else:
-            ga, dbias = split_bf16(g2, _use_lo()), None
+            ga, dbias = split_bf16(g2, want_lo, absmax_slot(g2) if f16 else None), None
         # dX = alpha * (dY . T);  d(alpha) = sum((dY . T) .* X) fused in the same epilogue
         if _want_packed(N) and packed_gemm_ok(M, ctx.packed_t):
             dx, dalpha = tgemm_packed(ga, ctx.packed_t, N, K, M, scale=al, dot_ref=x2)
@@ -454,8 +505,8 @@ class _TernaryLinearFn(torch.autograd.Function):
             dx, dalpha = tgemm(ga, ctx.ops_w_t, N, K, M, scale=al, dot_ref=x2)
         dw = None
         if ctx.ste:  # opt-in straight-through estimator: dW = G (dY and X consumed MN-major, no transposes)
-            xa = split_bf16(x2, _use_lo())
-            dw, _ = tgemm_dw_masked(ga + (1,), xa + (1,), M, K, N)
+            xa = split_bf16(x2, want_lo, absmax_slot(x2) if f16 else None)
+            dw, _ = tgemm_dw_masked(mn_view(ga), mn_view(xa), M, K, N)
         return dx.reshape(ctx.xshape), dw, dalpha, dbias, None
 
 
@@ -472,9 +523,9 @@ class _RPBLinearFn(torch.autograd.Function):
         if N == 0:
             y = x2.new_zeros((0, M))
         else:
-            xa = split_bf16(x2, _use_lo())
+            xa = split_operand(x2)
             y, _ = tgemm(xa, ops.w, N, M, K, scale=None, bias=None if bias is None else bias.detach())
-        # backward consumes the SAME bf16 hi/lo split of x (MN-major, as the dW B operand): save it
+        # backward consumes the SAME (hi, lo) split of x (MN-major, as the dW B operand): save it
         # instead of the fp32 activations (same bytes), so nothing is split or transposed twice
         if N == 0:
             ctx.save_for_backward(x2, mask)
@@ -483,6 +534,7 @@ class _RPBLinearFn(torch.autograd.Function):
         else:
             ctx.save_for_backward(xa[0], xa[1], mask)
         ctx.x_pitch = xa[2] if N else 0
+        ctx.x_slot = xa[4] if N else None
         ctx.n_tokens = N
         ctx.ops_w_t, ctx.packed = ops.w_t, ops.packed
         ctx.has_bias = bias is not None
@@ -502,11 +554,14 @@ class _RPBLinearFn(torch.autograd.Function):
         if N == 0:
             z = g2.new_zeros
             return (gy.new_zeros(ctx.xshape), z((M, K)), z(1), z(M) if ctx.has_bias else None, None, None)
-        xa = (saved[0], saved[1] if len(saved) == 3 else None, ctx.x_pitch)
+        xa = (saved[0], saved[1] if len(saved) == 3 else None, ctx.x_pitch, 0, ctx.x_slot)
+        f16 = xa[0].dtype == torch.float16
         if ctx.has_bias:  # ONE pass over dY: the split feeds both backward GEMMs, the column sums are d(bias)
-            ga, dbias = split_bf16_colsum(g2, xa[1] is not None)
+            ga, dbias = split_operand_colsum(g2, xa[1] is not None, f16)
         else:
-            ga, dbias = split_bf16(g2, xa[1] is not None), None
+            ga, dbias = split_bf16(g2, xa[1] is not None, absmax_slot(g2) if f16 else None), None
+            if len(ga) == 3:
+                ga = ga + (0, None)
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = tgemm(ga, ctx.ops_w_t, N, K, M)   # B = Wm [M, K] read MN-major
@@ -514,32 +569,39 @@ class _RPBLinearFn(torch.autograd.Function):
         # G = dY^T X with the mask and the d(alpha) reduction fused into the epilogue; dY [N, M] and
         # X [N, K] are consumed in place as MN-major operands
         mk = mask if mask.is_contiguous() else mask.contiguous()
-        dw, dalpha = tgemm_dw_masked(ga + (1,), xa + (1,), M, K, N, mask=mk, packed=ctx.packed)
+        dw, dalpha = tgemm_dw_masked(mn_view(ga), mn_view(xa), M, K, N, mask=mk, packed=ctx.packed)
         return dx, dw, dalpha, dbias, None, None
 
 
-def gelu_dropout_split(y: torch.Tensor, dropout_p: float, seed, want_lo: bool):
-    """d = dropout(gelu(y)) as a bf16 (hi, lo|None, pitch) GEMM operand; y contiguous fp32 [rows, cols], cols % 8 == 0."""
+def gelu_dropout_split(y: torch.Tensor, dropout_p: float, seed, want_lo: bool, slot=None):
+    """d = dropout(gelu(y)) as a (hi, lo|None, pitch, 0, slot) GEMM operand; y contiguous fp32 [rows, cols], cols % 8 == 0."""
     rows, cols = y.shape
     dev = nv.device_index(y)
-    hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device)
-    lo = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device) if want_lo else None
+    dt = torch.bfloat16 if slot is None else torch.float16
+    hi = torch.empty((rows, cols), dtype=dt, device=y.device)
+    lo = torch.empty((rows, cols), dtype=dt, device=y.device) if want_lo else None
     nv.call("atq_gelu_dropout_split", dev, y.data_ptr(), rows, cols, float(dropout_p), nv.ptr(seed), hi.data_ptr(), nv.ptr(lo),
-            nv.stream_ptr(dev))
-    return hi, lo, cols
+            nv.ptr(slot), nv.stream_ptr(dev))
+    return hi, lo, cols, 0, slot
 
 
-def gelu_dropout_bwd_split_colsum(g: torch.Tensor, y: torch.Tensor, dropout_p: float, seed, want_lo: bool):
-    """dy = g * keep/(1-p) * gelu'(y) as a bf16 operand + its column sums."""
+def gelu_dropout_bwd_split_colsum(g: torch.Tensor, y: torch.Tensor, dropout_p: float, seed, want_lo: bool, slot=None):
+    """dy = g * keep/(1-p) * gelu'(y) as a GEMM operand + its column sums."""
     rows, cols = y.shape
     dev = nv.device_index(y)
-    hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device)
-    lo = torch.empty((rows, cols), dtype=torch.bfloat16, device=y.device) if want_lo else None
+    dt = torch.bfloat16 if slot is None else torch.float16
+    hi = torch.empty((rows, cols), dtype=dt, device=y.device)
+    lo = torch.empty((rows, cols), dtype=dt, device=y.device) if want_lo else None
     out = torch.empty(cols, dtype=torch.float32, device=y.device)
     ws = nv.workspace(nv.lib.atq_workspace_bytes_split_colsum(rows, cols), y.device)
     nv.call("atq_gelu_dropout_bwd_split_colsum", dev, g.data_ptr(), y.data_ptr(), rows, cols, float(dropout_p), nv.ptr(seed),
-            hi.data_ptr(), nv.ptr(lo), out.data_ptr(), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
-    return (hi, lo, cols), out
+            hi.data_ptr(), nv.ptr(lo), out.data_ptr(), ws.data_ptr(), ws.numel(), nv.ptr(slot), nv.stream_ptr(dev))
+    return (hi, lo, cols, 0, slot), out
+
+
+def _keep_bound(p: float) -> float:
+    """Upper bound of the dropout keep factor 1/(1-p_eff) (p_eff is p rounded to 1/65536), with head-room."""
+    return 1.01 / max(1.0 - float(p) - 2.0 ** -16, 1e-6)
 
 
 class _RPBFFNFn(torch.autograd.Function):
@@ -555,14 +617,16 @@ class _RPBFFNFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         N = x2.shape[0]
-        lo = _use_lo()
-        xa = split_bf16(x2, lo)
+        lo, f16 = _use_lo(), _use_f16()
+        xa = split_operand(x2)
         y1, _ = tgemm(xa, ops1.w, N, H, K, bias=None if b1 is None else b1.detach())
-        da = gelu_dropout_split(y1, p, seed, lo)
+        # |dropout(gelu(y))| <= max|y| / (1-p): the hidden operand's scale comes from one reduction over y1
+        da = gelu_dropout_split(y1, p, seed, lo, absmax_slot(y1, _keep_bound(p)) if f16 else None)
         y2, _ = tgemm(da, ops2.w, N, M, H, bias=None if b2 is None else b2.detach())
         tensors = [y1, mask1, mask2, xa[0], da[0]] + ([xa[1], da[1]] if lo else [])
         ctx.save_for_backward(*tensors)
         ctx.seed = seed
+        ctx.slots = (xa[4], da[4])
         ctx.cfg = (N, K, H, M, float(p), lo, xa[2], b1 is not None, b2 is not None)
         ctx.ops = (ops1.w_t, ops1.packed, ops2.w_t, ops2.packed)
         ctx.xshape = x.shape
@@ -573,26 +637,28 @@ class _RPBFFNFn(torch.autograd.Function):
         N, K, H, M, p, lo, x_pitch, has_b1, has_b2 = ctx.cfg
         saved = ctx.saved_tensors
         y1, mask1, mask2 = saved[0], saved[1], saved[2]
-        xa = (saved[3], saved[5] if lo else None, x_pitch)
-        da = (saved[4], saved[6] if lo else None, H)
+        xa = (saved[3], saved[5] if lo else None, x_pitch, 0, ctx.slots[0])
+        da = (saved[4], saved[6] if lo else None, H, 0, ctx.slots[1])
+        f16 = saved[3].dtype == torch.float16
         w1_t, packed1, w2_t, packed2 = ctx.ops
         g2 = nv.require_f32(gy, "grad_output").reshape(-1, M)
         if not g2.is_contiguous():
             g2 = g2.contiguous()
         if has_b2:
-            ga2, db2 = split_bf16_colsum(g2, lo)
+            ga2, db2 = split_operand_colsum(g2, lo, f16)
         else:
-            ga2, db2 = split_bf16(g2, lo), None
+            ga2, db2 = split_bf16(g2, lo, absmax_slot(g2) if f16 else None), None
         dd, _ = tgemm(ga2, w2_t, N, H, M)  # gradient w.r.t. the dropped activations, fp32 [N, H]
         mk2 = mask2 if mask2.is_contiguous() else mask2.contiguous()
-        dw2, dalpha2 = tgemm_dw_masked(ga2 + (1,), da + (1,), M, H, N, mask=mk2, packed=packed2)
-        g1a, db1 = gelu_dropout_bwd_split_colsum(dd, y1, p, ctx.seed, lo)
+        dw2, dalpha2 = tgemm_dw_masked(mn_view(ga2), mn_view(da), M, H, N, mask=mk2, packed=packed2)
+        # |dd * keep/(1-p) * gelu'(y)| <= max|dd| * 1.13 / (1-p)
+        g1a, db1 = gelu_dropout_bwd_split_colsum(dd, y1, p, ctx.seed, lo, absmax_slot(dd, 1.13 * _keep_bound(p)) if f16 else None)
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = tgemm(g1a, w1_t, N, K, H)
             dx = dx.reshape(ctx.xshape)
         mk1 = mask1 if mask1.is_contiguous() else mask1.contiguous()
-        dw1, dalpha1 = tgemm_dw_masked(g1a + (1,), xa + (1,), H, K, N, mask=mk1, packed=packed1)
+        dw1, dalpha1 = tgemm_dw_masked(mn_view(g1a), mn_view(xa), H, K, N, mask=mk1, packed=packed1)
         return (dx, dw1, dalpha1, db1 if has_b1 else None, None, None, dw2, dalpha2, db2, None, None, None, None)
 
 

@@ -21,11 +21,12 @@ if not os.path.exists(_LIB_PATH):
         "(or `make -C atq-multimodal_b200/csrc`). The atq package has no CPU or eager fallback.")
 _lib = ctypes.CDLL(_LIB_PATH)
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class BF16Operand(Structure):
-    _fields_ = [("hi", c_void_p), ("lo", c_void_p), ("pitch", c_int64), ("mn_major", c_int32), ("reserved", c_int32)]
+    _fields_ = [("hi", c_void_p), ("lo", c_void_p), ("pitch", c_int64), ("mn_major", c_int32), ("format", c_int32),
+                ("inv_scale", c_void_p)]
 
 
 _P = c_void_p
@@ -52,13 +53,14 @@ _SIGS = {
     "atq_unpack2_to_bf16": (c_int, [c_int, _P, c_int64, _P, _P]),
     "atq_unpack2_to_i8": (c_int, [c_int, _P, c_int64, _P, _P]),
     "atq_route_mask_mul": (c_int, [c_int, _P, _P, _P, c_int64, _P, _P]),
-    "atq_split_bf16": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P]),
+    "atq_absmax_scale": (c_int, [c_int, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
+    "atq_split_bf16": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P]),
     "atq_workspace_bytes_split_colsum": (c_size_t, [c_int64, c_int64]),
-    "atq_split_bf16_colsum": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),
-    "atq_split_bf16_t": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P]),
-    "atq_build_ternary_operands": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P]),
+    "atq_split_bf16_colsum": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P, _P]),
+    "atq_split_bf16_t": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P, _P]),
+    "atq_build_ternary_operands": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, _P]),
     "atq_build_mixed_operands": (c_int, [c_int, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P,
-                                         c_int64, _P]),
+                                         c_int64, _P, _P]),
     "atq_workspace_bytes_tgemm": (c_size_t, [c_int64, c_int64]),
     "atq_tgemm": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P, _P,
                           c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
@@ -73,8 +75,8 @@ _SIGS = {
                                     _P, _P, c_int64, _P, _P, c_size_t, _P]),
     "atq_workspace_bytes_colsum": (c_size_t, [c_int64, c_int64]),
     "atq_colsum_f32": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
-    "atq_gelu_dropout_split": (c_int, [c_int, _P, c_int64, c_int64, c_float, _P, _P, _P, _P]),
-    "atq_gelu_dropout_bwd_split_colsum": (c_int, [c_int, _P, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "atq_gelu_dropout_split": (c_int, [c_int, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, _P]),
+    "atq_gelu_dropout_bwd_split_colsum": (c_int, [c_int, _P, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
     "atq_workspace_bytes_gated_residual": (c_size_t, [c_int64]),
     "atq_gated_residual_fwd": (c_int, [c_int, _P, _P, _P, c_int64, c_float, _P, _P, _P]),
     "atq_gated_residual_bwd": (c_int, [c_int, _P, _P, _P, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
@@ -159,6 +161,49 @@ def call(name: str, *args) -> None:
     check(getattr(_lib, name)(*args), name)
 
 
-def operand(hi: torch.Tensor, lo, pitch: int, mn_major: int = 0) -> BF16Operand:
-    """mn_major=1: the tensor is [kdim, rows] row-major (a row-major activation/weight used transposed)."""
-    return BF16Operand(hi.data_ptr(), None if lo is None else lo.data_ptr(), pitch, int(mn_major), 0)
+def operand(hi: torch.Tensor, lo, pitch: int, mn_major: int = 0, slot=None) -> BF16Operand:
+    """mn_major=1: the tensor is [kdim, rows] row-major (a row-major activation/weight used transposed).
+    The element format follows the tensor dtype (bfloat16 / float16); `slot` is the scale slot of a scaled-fp16
+    operand (4 floats; slot[2] = 1/scale is handed to the GEMM epilogue)."""
+    fmt = 1 if hi.dtype == torch.float16 else 0
+    return BF16Operand(hi.data_ptr(), None if lo is None else lo.data_ptr(), pitch, int(mn_major), fmt,
+                       None if slot is None else slot.data_ptr() + 8)
+
+
+_SLOT_ARENAS: dict = {}
+_ARENAS_USED_IN_CAPTURE: list = []   # never freed: a captured graph keeps raw pointers into them
+_ARENA_FLOATS = 1 << 16              # 16 384 slots
+
+
+def new_slot(device) -> torch.Tensor:
+    """A zeroed 4-float scale slot (include/atq_sm100.h: atq_absmax_scale), carved from a per-device arena so that
+    handing one out costs no kernel launch; slots are never handed out twice.  Arenas are allocated outside
+    CUDA-graph capture (ordinary allocator memory) and, once a capture has drawn from one, kept alive for the life
+    of the process, because graph replays write through the raw pointers."""
+    key = (device.type, device.index)
+    capturing = torch.cuda.is_current_stream_capturing()
+    arena = _SLOT_ARENAS.get(key)
+    low = arena is None or arena[1] + 4 > arena[0].numel() or (not capturing and arena[1] > arena[0].numel() // 2 and arena[2])
+    if low:
+        # (inside a capture this allocation lands in the graph's private pool; it is pinned below like the others)
+        arena = [torch.zeros(_ARENA_FLOATS, dtype=torch.float32, device=device), 0, False]
+        _SLOT_ARENAS[key] = arena
+    if capturing and not arena[2]:
+        arena[2] = True
+        _ARENAS_USED_IN_CAPTURE.append(arena[0])
+    off = arena[1]
+    arena[1] = off + 4
+    return arena[0][off: off + 4]
+
+
+_UNIT_SLOTS: dict = {}
+
+
+def unit_slot(device) -> torch.Tensor:
+    """Scale slot with scale 1 (exactly representable operands such as ternary weights in fp16)."""
+    key = (device.type, device.index)
+    s = _UNIT_SLOTS.get(key)
+    if s is None:
+        s = torch.tensor([0.0, 1.0, 1.0, 0.0], dtype=torch.float32, device=device)
+        _UNIT_SLOTS[key] = s
+    return s

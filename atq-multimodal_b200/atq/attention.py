@@ -41,7 +41,7 @@ def _rows(t: torch.Tensor, name: str):
 
 
 def _terms() -> int:
-    return 3 if eng.get_gemm_mode() == "parity" else 1
+    return 3 if eng.get_gemm_mode() != "fast" else 1
 
 
 class _AttentionCoreFn(torch.autograd.Function):

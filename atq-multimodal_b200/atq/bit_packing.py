@@ -63,13 +63,16 @@ class TernaryBitPacking:
         x2 = x.reshape(-1, K)
         if x2.shape[0] == 0:
             return x.new_zeros(*x.shape[:-1], M) * alpha
-        xa = eng.split_bf16(x2, eng.get_gemm_mode() == "parity")
+        xa = eng.split_operand(x2)
+        f16 = xa[0].dtype == torch.float16
         packed = packed.contiguous()
         if eng.packed_gemm_ok(K, packed) and eng._PACKED != "never":
             # the GEMM reads the codec bytes and expands them in shared memory
             y, _ = eng.tgemm_packed(xa, packed, x2.shape[0], M, K)
         else:
             tb = eng.unpack2(packed, M * K, torch.bfloat16).view(M, K)
+            if f16:
+                tb = tb.to(torch.float16)  # -1 / 0 / +1: exact in either 16-bit format
             pitch = nv.round_up(K, 8)
             if pitch != K:
                 tb = torch.nn.functional.pad(tb, (0, pitch - K))

@@ -159,13 +159,14 @@ class PackedTernaryLinear(nn.Module):
         N = x2.shape[0]
         if N == 0:
             return x2.new_zeros((*x.shape[:-1], M))
-        xa = eng.split_bf16(x2, eng.get_gemm_mode() == "parity")
+        xa = eng.split_operand(x2)
         if eng.packed_gemm_ok(K, self.packed_weights):
             y, _ = eng.tgemm_packed(xa, self.packed_weights, N, M, K, scale=self.alpha, bias=self.bias)
         else:
-            if self._tb is None or self._tb[0].device != x2.device:
+            f16 = xa[0].dtype == torch.float16
+            if self._tb is None or self._tb[0].device != x2.device or (self._tb[0].dtype == torch.float16) != f16:
                 t = eng.unpack2(self.packed_weights, M * K, torch.float32).reshape(M, K)
-                self._tb = eng.split_bf16(t, False)
+                self._tb = eng.split_bf16(t, False, nv.unit_slot(t.device) if f16 else None)  # T is exact in either format
             y, _ = eng.tgemm(xa, self._tb, N, M, K, scale=self.alpha, bias=self.bias)
         return y.reshape(*x.shape[:-1], M)
 
@@ -197,7 +198,7 @@ class PackedRPBLinear(nn.Module):
             M, K = self.out_features, self.in_features
             wm = eng.unpack2(self.packed_weights, M * K, torch.float32) * self.alpha  # alpha * T
             wm[self.residual_index.long()] = self.residual_value                      # fp32 weights under the mask
-            self._w = eng.split_bf16(wm.reshape(M, K), mode == "parity")
+            self._w = eng.split_operand(wm.reshape(M, K))
             self._mode = mode
         return self._w
 
@@ -212,7 +213,7 @@ class PackedRPBLinear(nn.Module):
         N = x2.shape[0]
         if N == 0:
             return x2.new_zeros((*x.shape[:-1], M))
-        xa = eng.split_bf16(x2, eng.get_gemm_mode() == "parity")
+        xa = eng.split_operand(x2)
         y, _ = eng.tgemm(xa, self._operand(x2.device), N, M, K, bias=self.bias)
         return y.reshape(*x.shape[:-1], M)
 

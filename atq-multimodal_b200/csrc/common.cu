@@ -52,7 +52,7 @@ int sm_count(int device) {
 
 extern "C" {
 
-int atq_abi_version(void) { return 5; }
+int atq_abi_version(void) { return 6; }
 
 const char* atq_last_error_string(void) { return atq::last_error_buf(); }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -107,6 +108,46 @@ __device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) 
   float hf = bf16_bits_to_float(hi);
   float r = x - hf;
   lo = (fabsf(hf) <= 3.3895313892515355e38f) ? bf16_bits(r) : (uint16_t)0;
+}
+
+// GEMM operand element format.  bf16: (hi, lo) = (bf16(x), bf16(x - hi)), ~16 significant bits.
+// scaled fp16: (hi, lo) = (fp16(s x), fp16(s x - hi)) with ONE power-of-two scale s per tensor chosen so that
+// max|s x| lies in [2^14, 2^15): ~22 significant bits for every element within 2^-18 of the tensor's maximum and an
+// absolute error below 2^-40 max|x| for the rest; the GEMM epilogue multiplies by 1/s (exact).  Same MMA count as
+// the bf16 pair, 2^5 times the precision: this is what lets a whole network's gradients track the fp32 reference.
+// Scale slot (4 floats, caller-owned): [0] bits of max|x| (scratch), [1] s, [2] 1/s, [3] ticket (scratch).
+struct OperandFmt {
+  float scale;
+  int f16;
+};
+__device__ __forceinline__ OperandFmt load_fmt(const float* slot, int force_f16 = 0) {
+  OperandFmt f;
+  f.f16 = (slot != nullptr) || force_f16;
+  f.scale = slot != nullptr ? __ldg(slot + 1) : 1.f;
+  return f;
+}
+__device__ __forceinline__ void split2(const OperandFmt& f, float x, uint16_t& hi, uint16_t& lo) {
+  if (f.f16) {
+    const float xs = x * f.scale;
+    const __half h = __float2half_rn(xs);
+    const float hf = __half2float(h);
+    hi = __half_as_ushort(h);
+    lo = (fabsf(hf) <= 65504.f) ? __half_as_ushort(__float2half_rn(xs - hf)) : (uint16_t)0;
+  } else {
+    split_bf16(x, hi, lo);
+  }
+}
+// power-of-two scale that maps a bound b >= max|x| into [2^14, 2^15); (1, 1) for b = 0 / inf / nan
+__device__ __forceinline__ void pow2_scale_for(float b, float& scale, float& inv) {
+  const uint32_t e = (__float_as_uint(b) >> 23) & 0xFFu;
+  if (e == 0u || e == 255u) {
+    scale = 1.f; inv = 1.f;
+    return;
+  }
+  int se = 268 - (int)e;  // biased exponent of the scale
+  se = se < 1 ? 1 : (se > 253 ? 253 : se);
+  scale = __uint_as_float((uint32_t)se << 23);
+  inv = __uint_as_float((uint32_t)(254 - se) << 23);
 }
 
 // Counter-based dropout (shared by the attention kernels and the fused FFN activation): one 32-bit hash per

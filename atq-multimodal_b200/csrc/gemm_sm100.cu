@@ -42,6 +42,31 @@ __device__ __forceinline__ uint32_t bf16x2_fma(uint32_t a, uint32_t b, uint32_t 
   asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+__device__ __forceinline__ uint32_t f16x2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// fp16 flavour of the same trick: (0x6400 | c << sh) == 1024 + c * 2^sh exactly (10 mantissa bits), one f16x2 FMA -> c - 1
+__device__ __forceinline__ void unpack16_to_f16(uint32_t w, uint4& lo8, uint4& hi8) {
+  constexpr uint32_t kMagic = 0x64006400u;  // 1024.0, 1024.0
+  constexpr uint32_t kS0 = 0x3C003C00u, kB0 = 0xE401E401u;  // * 1      - 1025
+  constexpr uint32_t kS2 = 0x34003400u, kB2 = 0xDC04DC04u;  // * 0.25   - 257
+  constexpr uint32_t kS4 = 0x2C002C00u, kB4 = 0xD410D410u;  // * 0.0625 - 65
+  const uint32_t x1 = w >> 6, x2 = w >> 12;
+  const uint32_t a0 = f16x2_fma((w & 0x00030003u) | kMagic, kS0, kB0);
+  const uint32_t a1 = f16x2_fma((w & 0x000C000Cu) | kMagic, kS2, kB2);
+  const uint32_t a2 = f16x2_fma((w & 0x00300030u) | kMagic, kS4, kB4);
+  const uint32_t a3 = f16x2_fma((x1 & 0x00030003u) | kMagic, kS0, kB0);
+  const uint32_t a4 = f16x2_fma((x1 & 0x000C000Cu) | kMagic, kS2, kB2);
+  const uint32_t a5 = f16x2_fma((x1 & 0x00300030u) | kMagic, kS4, kB4);
+  const uint32_t a6 = f16x2_fma((x2 & 0x00030003u) | kMagic, kS0, kB0);
+  const uint32_t a7 = f16x2_fma((x2 & 0x000C000Cu) | kMagic, kS2, kB2);
+  lo8 = make_uint4(__byte_perm(a0, a1, 0x5410), __byte_perm(a2, a3, 0x5410), __byte_perm(a4, a5, 0x5410),
+                   __byte_perm(a6, a7, 0x5410));
+  hi8 = make_uint4(__byte_perm(a0, a1, 0x7632), __byte_perm(a2, a3, 0x7632), __byte_perm(a4, a5, 0x7632),
+                   __byte_perm(a6, a7, 0x7632));
+}
 __device__ __forceinline__ void unpack16_to_bf16(uint32_t w, uint4& lo8, uint4& hi8) {
   constexpr uint32_t kMagic = 0x43004300u;  // 128.0, 128.0
   constexpr uint32_t kS0 = 0x3F803F80u, kB0 = 0xC301C301u;  // * 1      - 129
@@ -82,6 +107,9 @@ struct GemmParams {
   int64_t b_packed_pitch;   // bytes per row (= kdim / 4)
   int splits;               // split-K: work item = (tile, k-range); range s writes out + s * split_stride
   int64_t split_stride;     // elements
+  const float* inv_a;       // nullable device scalars: 1/scale of a scaled-fp16 operand (exact powers of two);
+  const float* inv_b;       //   the accumulator is multiplied by both before anything else in the epilogue
+  int f16;                  // operands are fp16 (both), else bf16
 };
 
 constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp [32][36] fp32 transposition buffers (rows 16-byte aligned)
@@ -93,7 +121,9 @@ struct GemmCfg {
   static constexpr int kStageBytes = NUM_A * kABytes + NUM_B * kBBytes;
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kTmemCols = 2 * BLOCK_N;  // double-buffered accumulator
+  static constexpr bool kDual = (NUM_A + NUM_B > 2);
+  static constexpr int kAccCols = (kDual ? 2 : 1) * BLOCK_N;
+  static constexpr int kTmemCols = 2 * kAccCols;  // double-buffered
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
@@ -115,6 +145,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
   static_assert(BK == 64 || BK == 32, "BLOCK_K is 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows)");
   static_assert(!(B_PACKED && BK != 64), "the converter writes 128-byte rows");
   constexpr int kMnBlock = BK * 128;  // bytes of one [BK k x 64 mn] MN-major block
+  constexpr bool kDual = Cfg::kDual;             // an operand has a lo part: second accumulator for the corrections
+  constexpr int kAccCols = Cfg::kAccCols;        // TMEM columns per tile (1 or 2 accumulators)
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -208,7 +240,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
   } else if (warp_idx == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BLOCK_N, A_MN, B_MN>();
+      // a/b format fields (bits 7-9, 10-12): 1 = bf16, 0 = fp16
+      const uint32_t idesc = p.f16 ? (make_idesc<BLOCK_N, A_MN, B_MN>() & ~((7u << 7) | (7u << 10))) : make_idesc<BLOCK_N, A_MN, B_MN>();
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -217,8 +250,15 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tmem_empty_bar(a), aphase ^ 1u);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N);
-        uint32_t accumulate = 0;
+        // Two accumulators per tile when an operand has a lo part.  tcgen05 accumulates in fp32 with truncation:
+        // every instruction rounds the WHOLE accumulator once (<= 1 ulp toward zero, however small the addend;
+        // measured ~4e-8 relative per instruction, 1.7e-5 at k = 4096 with three interleaved terms).  The
+        // correction terms (lo x hi, hi x lo; ~2^-11 of the result) therefore go to their own accumulator, whose
+        // roundings are 2^-11 as large, and the hi x hi accumulator is rounded k/16 times instead of 2-3 k/16
+        // times; the epilogue adds the two in fp32 (round to nearest).
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * kAccCols);
+        const uint32_t tmem_cor = tmem_acc + (uint32_t)BLOCK_N;
+        uint32_t accumulate = 0, accumulate_cor = 0;
         for (int kb = kb_lo(w); kb < kb_hi(w); ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
@@ -237,8 +277,14 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
             const uint64_t kob = (uint64_t)(B_MN ? (k * UMMA_K * 128) >> 4 : (k * UMMA_K * 2) >> 4);
             umma_bf16(tmem_acc, da_hi + koa, db_hi + kob, idesc, accumulate);
             accumulate = 1;
-            if (NUM_A == 2) umma_bf16(tmem_acc, da_lo + koa, db_hi + kob, idesc, 1u);
-            if (NUM_B == 2) umma_bf16(tmem_acc, da_hi + koa, db_lo + kob, idesc, 1u);
+            if (NUM_A == 2) {
+              umma_bf16(tmem_cor, da_lo + koa, db_hi + kob, idesc, accumulate_cor);
+              accumulate_cor = 1;
+            }
+            if (NUM_B == 2) {
+              umma_bf16(tmem_cor, da_hi + koa, db_lo + kob, idesc, accumulate_cor);
+              accumulate_cor = 1;
+            }
           }
           umma_commit(empty_bar(stage));  // frees this smem stage once the MMAs above retire
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -284,7 +330,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 lo8, hi8;
-            unpack16_to_bf16(words[q], lo8, hi8);
+            if (p.f16) unpack16_to_f16(words[q], lo8, hi8);
+            else unpack16_to_bf16(words[q], lo8, hi8);
             st_shared_v4(row_addr + (((uint32_t)(2 * q) ^ sw) << 4), lo8);
             st_shared_v4(row_addr + (((uint32_t)(2 * q + 1) ^ sw) << 4), hi8);
           }
@@ -308,6 +355,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     const int quarter = warp_idx & 3;  // TMEM lane quarter this warp may access
     float* stg = reinterpret_cast<float*>(smem_gen + kStages * Cfg::kStageBytes) + (warp_idx - 2) * (32 * 36);
     const float scale = (EPI == EPI_LINEAR && p.scale != nullptr) ? __ldg(p.scale) : 1.f;
+    // 1/(s_a s_b) of scaled-fp16 operands: exact power of two, applied to the raw accumulator first
+    const float opscale = (p.inv_a != nullptr ? __ldg(p.inv_a) : 1.f) * (p.inv_b != nullptr ? __ldg(p.inv_b) : 1.f);
     float partial = 0.f;
     // 128-bit path: every lane owns 4 consecutive columns of 8 rows per chunk (4x fewer shared/global
     // instructions than lane = column); needs 16-byte aligned rows on every tensor the epilogue touches
@@ -335,7 +384,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       // accumulator: chunk 0 is fetched BEFORE waiting for the MMAs and chunk ch+1 while chunk ch is
       // processed, so short GEMMs do not pay one memory latency per chunk after the mainloop.
       const bool side = (EPI == EPI_MASKED) || p.dot_ref != nullptr;
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BLOCK_N) + ((uint32_t)(quarter * 32) << 16);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(a * kAccCols) + ((uint32_t)(quarter * 32) << 16);
       if (vec_ok) {
         // ---- 128-bit path ----
         auto load_side_v = [&](int ch, float4 (&f)[8], uint32_t (&cd)[8]) {
@@ -368,10 +417,16 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
         for (int ch = 0; ch < nch; ++ch) {
           uint32_t acc[32];
           tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(ch * 32), acc);
+          uint32_t cor[kDual ? 32 : 1];
+          if constexpr (kDual) tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(BLOCK_N + ch * 32), cor);
           float4 nf[8];
           uint32_t nc[8];
           if (side && ch + 1 < nch) load_side_v(ch + 1, nf, nc);
           tmem_ld_wait();
+          if constexpr (kDual) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(cor[j]));
+          }
           if (ch == nch - 1) {  // everything this warp needs has left TMEM: hand the buffer back
             tcgen05_fence_before();
             if (lane == 0) mbar_arrive(tmem_empty_bar(a));
@@ -391,7 +446,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
           for (int g = 0; g < 8; ++g) {
             const int row = 4 * g + vrg;
             if (col_ok && row < rows_here) {
-              const float4 v = *reinterpret_cast<const float4*>(stg + row * 36 + 4 * vq);
+              float4 v = *reinterpret_cast<const float4*>(stg + row * 36 + 4 * vq);
+              v.x *= opscale; v.y *= opscale; v.z *= opscale; v.w *= opscale;
               float4 o;
               if constexpr (EPI == EPI_LINEAR) {
                 if (p.dot_ref != nullptr) partial += (v.x * vf[g].x + v.y * vf[g].y) + (v.z * vf[g].z + v.w * vf[g].w);
@@ -429,7 +485,13 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       for (int ch = 0; ch < nch; ++ch) {
         uint32_t acc[32];
         tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(ch * 32), acc);
+        uint32_t cor[kDual ? 32 : 1];
+        if constexpr (kDual) tmem_ld_32x32b_x32(tmem_acc + (uint32_t)(BLOCK_N + ch * 32), cor);
         tmem_ld_wait();
+        if constexpr (kDual) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(cor[j]));
+        }
         if (ch == nch - 1) {
           tcgen05_fence_before();
           if (lane == 0) mbar_arrive(tmem_empty_bar(a));
@@ -442,7 +504,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
           const float bias = (EPI == EPI_LINEAR && p.bias != nullptr) ? __ldg(p.bias + c) : 0.f;
 #pragma unroll 4
           for (int rr = 0; rr < rows_here; ++rr) {
-            const float v = stg[rr * 36 + lane];
+            const float v = stg[rr * 36 + lane] * opscale;
             if constexpr (EPI == EPI_LINEAR) {
               if (p.dot_ref != nullptr) partial += v * __ldg(p.dot_ref + (r_base + rr) * p.dot_ref_pitch + c);
               out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
@@ -604,6 +666,10 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
   mb_lo = mb_hi;
   if (NUM_A == 2 && (r = map_a(&ma_lo, a->lo)) != ATQ_OK) return r;
   if (NUM_B == 2 && (r = map_b(&mb_lo, b->lo)) != ATQ_OK) return r;
+  GemmParams pp = p;
+  pp.f16 = a->format != 0;
+  pp.inv_a = a->inv_scale;
+  pp.inv_b = B_PACKED ? nullptr : b->inv_scale;
   auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED, LAYOUT, BK>;
   static bool attr_done_dev[64] = {false};  // per instantiation, per device
   int dev = 0;
@@ -626,7 +692,7 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
   const int64_t work = tiles * (p.splits > 1 ? p.splits : 1);
   const int grid = (int)(work < sms ? work : sms);
   *grid_used = grid;
-  kern<<<grid, gemm_threads(B_PACKED, BLOCK_N), Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  kern<<<grid, gemm_threads(B_PACKED, BLOCK_N), Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pp);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("tgemm launch failed: %s", cudaGetErrorString(e));
@@ -649,24 +715,12 @@ static int dispatch_layout(const atq_bf16_operand* a, const atq_bf16_operand* b,
     if (b2) ATQ_GO(1, 2, 64);
     ATQ_GO(1, 1, 64);
   }
-  if (a2 && b2) {
-    // three MMA terms: at BLOCK_N = 128 every tcgen05.mma reads 8 KB of shared memory per 64 cycles (the
-    // 128 B/cycle limit, 82 % tensor-pipe activity measured); 256-wide tiles need 12 KB per 128 cycles.
-    // BLOCK_K = 32 (SWIZZLE_64B rows) keeps four 48 KB stages in shared memory.
-    // ... but only when the wide tiles still fill the machine (small-output / long-K GEMMs such as dW
-    // prefer more, narrower tiles)
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int64_t tiles256 = ((p.cols + 255) / 256) * ((p.rows + BLOCK_M - 1) / BLOCK_M) * (p.splits > 1 ? p.splits : 1);
-    if (mid || tiles256 < sm_count(dev)) ATQ_GO(2, 2, 128);
-    return launch_cfg<2, 2, 256, EPI, false, LAYOUT, 32>(a, b, p, stream, grid_used);
-  }
+  // operands with a lo part keep two accumulators per tile (hi x hi, corrections): 4 x BLOCK_N TMEM columns
+  // double-buffered, so those kernels use 128-wide tiles; single-term GEMMs use 256-wide tiles when wide enough
+  if (a2 && b2) ATQ_GO(2, 2, 128);
   if (b2) ATQ_GO(1, 2, 128);
-  if (mid) {
-    if (a2) ATQ_GO(2, 1, 128);
-    ATQ_GO(1, 1, 128);
-  }
-  if (a2) ATQ_GO(2, 1, 256);
+  if (a2) ATQ_GO(2, 1, 128);
+  if (mid) ATQ_GO(1, 1, 128);
   ATQ_GO(1, 1, 256);
 #undef ATQ_GO
 }
@@ -688,6 +742,10 @@ static int check_operand(const atq_bf16_operand* o, const char* name) {
   }
   if ((o->pitch % 8) != 0 || (reinterpret_cast<uintptr_t>(o->hi) & 15u) || (o->lo && (reinterpret_cast<uintptr_t>(o->lo) & 15u))) {
     set_error("tgemm: operand %s needs pitch %% 8 == 0 and 16-byte aligned pointers", name);
+    return ATQ_EINVAL;
+  }
+  if (o->format != 0 && o->format != 1) {
+    set_error("tgemm: operand %s has unknown element format %d (0 = bf16, 1 = fp16)", name, (int)o->format);
     return ATQ_EINVAL;
   }
   return ATQ_OK;
@@ -717,6 +775,7 @@ int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf
   ATQ_CHECK_ARG(a->pitch >= (a->mn_major ? rows : kdim) && b->pitch >= (b->mn_major ? cols : kdim),
                 "operand pitch smaller than its contiguous extent");
   ATQ_CHECK_ARG((dot_ref == nullptr) == (dot_out == nullptr), "dot_ref and dot_out go together");
+  ATQ_CHECK_ARG(a->format == b->format, "A and B operands must have the same element format (tcgen05 kind::f16)");
   if (dot_out != nullptr && (ws == nullptr || ws_bytes < atq_workspace_bytes_tgemm(rows, cols))) {
     set_error("atq_tgemm: workspace too small");
     return ATQ_EWORKSPACE;
@@ -766,12 +825,12 @@ int atq_tgemm_packed(int device, int64_t rows, int64_t cols, int64_t kdim, const
   p.b_packed = b_packed; p.b_packed_pitch = kdim / 4;
   int grid = 0;
   const bool a2 = a->lo != nullptr;
-  if (cols <= 128) {
-    r = a2 ? launch_cfg<2, 1, 128, EPI_LINEAR, true>(a, nullptr, p, stream, &grid)
-           : launch_cfg<1, 1, 128, EPI_LINEAR, true>(a, nullptr, p, stream, &grid);
+  if (a2) {
+    r = launch_cfg<2, 1, 128, EPI_LINEAR, true>(a, nullptr, p, stream, &grid);  // two accumulators per tile
+  } else if (cols <= 128) {
+    r = launch_cfg<1, 1, 128, EPI_LINEAR, true>(a, nullptr, p, stream, &grid);
   } else {
-    r = a2 ? launch_cfg<2, 1, 256, EPI_LINEAR, true>(a, nullptr, p, stream, &grid)
-           : launch_cfg<1, 1, 256, EPI_LINEAR, true>(a, nullptr, p, stream, &grid);
+    r = launch_cfg<1, 1, 256, EPI_LINEAR, true>(a, nullptr, p, stream, &grid);
   }
   if (r != ATQ_OK) return r;
   if (dot_out) {
@@ -827,6 +886,7 @@ int atq_tgemm_dw_masked(int device, int64_t out_features, int64_t in_features, i
   ATQ_CHECK_ARG(dy_t->pitch >= (dy_t->mn_major ? out_features : n_tokens) && x_t->pitch >= (x_t->mn_major ? in_features : n_tokens),
                 "operand pitch smaller than its contiguous extent");
   ATQ_CHECK_ARG((packed == nullptr) == (dalpha_out == nullptr), "packed and dalpha_out go together");
+  ATQ_CHECK_ARG(dy_t->format == x_t->format, "dY and X operands must have the same element format");
   ATQ_ENSURE_DEVICE(device);
   cudaStream_t stream = (cudaStream_t)stream_;
   const size_t part_bytes = atq_workspace_bytes_tgemm(out_features, in_features) + 4096;

@@ -286,11 +286,64 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------
-// fp32 -> bf16 hi/lo split, row-major, for the GEMM A operands
+// Per-tensor power-of-two scale for the scaled-fp16 operand format (common.cuh: OperandFmt).
+// One launch: every CTA folds max|x| of its share into slot[0] (atomicMax on the bit pattern, valid for
+// non-negative floats); the last CTA to finish (ticket in slot[3]) derives the scale from
+// bound = max(max|x|, |*extra|) * bound_mul, stores {scale, 1/scale} in slot[1..2] and re-arms slot[0] = slot[3] = 0
+// so that a CUDA-graph replay of the same launch starts clean.  NaNs are ignored by fmaxf; an infinite
+// maximum yields scale 1 (the operand then carries the infinities, as the fp32 reference would).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+    absmax_scale_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld, float bound_mul,
+                        const float* __restrict__ extra, float* __restrict__ slot, int vec) {
+  float m = 0.f;
+  if (vec) {  // contiguous, 16-byte aligned: flat float4 walk
+    const int64_t n = rows * cols, n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n4; g += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + g);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      for (int64_t i = n4 * 4; i < n; ++i) m = fmaxf(m, fabsf(x[i]));
+  } else {
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
+      for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) m = fmaxf(m, fabsf(__ldg(x + r * ld + c)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s_m[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) m = fmaxf(m, s_m[i]);
+    unsigned int* bits = reinterpret_cast<unsigned int*>(slot);
+    atomicMax(bits, __float_as_uint(m));
+    __threadfence();
+    const unsigned int ticket = atomicAdd(bits + 3, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      float b = __uint_as_float(atomicExch(bits, 0u));  // read the maximum and re-arm
+      if (extra != nullptr) b = fmaxf(b, fabsf(__ldg(extra)));
+      b *= bound_mul;
+      float sc, inv;
+      pow2_scale_for(b, sc, inv);
+      slot[1] = sc;
+      slot[2] = inv;
+      bits[3] = 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// fp32 -> (hi, lo) operand split (bf16 pair, or scaled fp16 pair when a scale slot is given), row-major
 // ------------------------------------------------------------------------------------
 template <bool HAS_LO>
 __global__ void __launch_bounds__(kThreads)
-    split_flat_kernel(const float* __restrict__ x, int64_t n, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
+    split_flat_kernel(const float* __restrict__ x, int64_t n, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                      const float* __restrict__ fslot) {
+  const OperandFmt fmt = load_fmt(fslot);
   // contiguous case (ld_in == cols == pitch): n % 8 == 0 guaranteed by the caller
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -307,7 +360,7 @@ __global__ void __launch_bounds__(kThreads)
       int64_t g = g0 + j * stride;
       if (g >= n4) continue;
       uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-      split_bf16(v[j].x, h0, l0); split_bf16(v[j].y, h1, l1); split_bf16(v[j].z, h2, l2); split_bf16(v[j].w, h3, l3);
+      split2(fmt, v[j].x, h0, l0); split2(fmt, v[j].y, h1, l1); split2(fmt, v[j].z, h2, l2); split2(fmt, v[j].w, h3, l3);
       *reinterpret_cast<uint2*>(hi + 4 * g) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
       if constexpr (HAS_LO)
         *reinterpret_cast<uint2*>(lo + 4 * g) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
@@ -322,7 +375,8 @@ __global__ void __launch_bounds__(kThreads)
 template <bool HAS_LO>
 __global__ void __launch_bounds__(kThreads)
     split_colsum_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, uint16_t* __restrict__ hi,
-                        uint16_t* __restrict__ lo, float* __restrict__ part, int64_t R) {
+                        uint16_t* __restrict__ lo, float* __restrict__ part, int64_t R, const float* __restrict__ fslot) {
+  const OperandFmt fmt = load_fmt(fslot);
   const int64_t cg4 = cols >> 2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cg4 * R) return;
@@ -341,7 +395,7 @@ __global__ void __launch_bounds__(kThreads)
       if (r >= rows) continue;
       const int64_t g = r * cg4 + cg;
       uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-      split_bf16(v[j].x, h0, l0); split_bf16(v[j].y, h1, l1); split_bf16(v[j].z, h2, l2); split_bf16(v[j].w, h3, l3);
+      split2(fmt, v[j].x, h0, l0); split2(fmt, v[j].y, h1, l1); split2(fmt, v[j].z, h2, l2); split2(fmt, v[j].w, h3, l3);
       *reinterpret_cast<uint2*>(hi + 4 * g) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
       if constexpr (HAS_LO)
         *reinterpret_cast<uint2*>(lo + 4 * g) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
@@ -374,7 +428,9 @@ __device__ __forceinline__ float gelu_grad(float x) {
 template <bool BWD, bool HAS_LO>
 __global__ void __launch_bounds__(kThreads)
     act_split_kernel(const float* __restrict__ x, const float* __restrict__ y, int64_t rows, int64_t cols,
-                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ part, int64_t R, const ActParams ap) {
+                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, float* __restrict__ part, int64_t R, const ActParams ap,
+                     const float* __restrict__ fslot) {
+  const OperandFmt fmt = load_fmt(fslot);
   const int64_t cg4 = cols >> 2;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= cg4 * R) return;
@@ -416,7 +472,7 @@ __global__ void __launch_bounds__(kThreads)
         o = make_float4(gelu_fwd(v[j].x) * k0, gelu_fwd(v[j].y) * k1, gelu_fwd(v[j].z) * k2, gelu_fwd(v[j].w) * k3);
       }
       uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-      split_bf16(o.x, h0, l0); split_bf16(o.y, h1, l1); split_bf16(o.z, h2, l2); split_bf16(o.w, h3, l3);
+      split2(fmt, o.x, h0, l0); split2(fmt, o.y, h1, l1); split2(fmt, o.z, h2, l2); split2(fmt, o.w, h3, l3);
       *reinterpret_cast<uint2*>(hi + 4 * g) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
       if constexpr (HAS_LO)
         *reinterpret_cast<uint2*>(lo + 4 * g) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
@@ -567,13 +623,14 @@ __global__ void adamw_advance_kernel(float* step_p) { *step_p += 1.f; }
 template <bool HAS_LO>
 __global__ void __launch_bounds__(kThreads)
     split_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
-                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pitch) {
+                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pitch, const float* __restrict__ fslot) {
+  const OperandFmt fmt = load_fmt(fslot);
   // general strided case: one row per CTA step, scalar coalesced accesses
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
     const float* xr = x + r * ld_in;
     for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
       uint16_t h, l;
-      split_bf16(__ldg(xr + c), h, l);
+      split2(fmt, __ldg(xr + c), h, l);
       hi[r * pitch + c] = h;
       if constexpr (HAS_LO) lo[r * pitch + c] = l;
     }
@@ -585,7 +642,8 @@ constexpr int kTile = 64;
 template <bool HAS_LO>
 __global__ void __launch_bounds__(256)
     split_t_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
-                   uint16_t* __restrict__ hi_t, uint16_t* __restrict__ lo_t, int64_t pitch_t) {
+                   uint16_t* __restrict__ hi_t, uint16_t* __restrict__ lo_t, int64_t pitch_t, const float* __restrict__ fslot) {
+  const OperandFmt fmt = load_fmt(fslot);
   __shared__ float tile[kTile][kTile + 1];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
   const int64_t c0 = (int64_t)blockIdx.x * kTile, r0 = (int64_t)blockIdx.y * kTile;
@@ -600,7 +658,7 @@ __global__ void __launch_bounds__(256)
     int64_t c = c0 + cc, r = r0 + tx;
     if (c < cols && r < rows) {
       uint16_t h, l;
-      split_bf16(tile[tx][cc], h, l);
+      split2(fmt, tile[tx][cc], h, l);
       hi_t[c * pitch_t + r] = h;
       if constexpr (HAS_LO) lo_t[c * pitch_t + r] = l;
     }
@@ -619,8 +677,9 @@ __global__ void __launch_bounds__(256)
                           uint8_t* __restrict__ packed, uint8_t* __restrict__ packed_t,
                           uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pitch,
                           uint16_t* __restrict__ hi_t, uint16_t* __restrict__ lo_t, int64_t pitch_t,
-                          TernStats* __restrict__ stats) {
-  __shared__ float tile[kTile][kTile + 1];      // value that goes to the bf16 operands
+                          TernStats* __restrict__ stats, const float* __restrict__ fslot, int force_f16) {
+  const OperandFmt fmt = load_fmt(fslot, force_f16);
+  __shared__ float tile[kTile][kTile + 1];      // value that goes to the bf16 / fp16 operands
   __shared__ uint8_t codes[kTile][kTile + 4];   // 2-bit codes of T (for the codec bytes)
   const float thr = __ldg(thr_p);
   const float alpha = MIXED ? __ldg(alpha_p) : 1.f;
@@ -658,7 +717,7 @@ __global__ void __launch_bounds__(256)
       }
       if (hi != nullptr) {
         uint16_t h, l;
-        split_bf16(val, h, l);
+        split2(fmt, val, h, l);
         hi[m * pitch + k] = h;
         if (MIXED && lo != nullptr) lo[m * pitch + k] = l;
       }
@@ -694,7 +753,7 @@ __global__ void __launch_bounds__(256)
       int64_t k = k0 + cc, m = m0 + tx;
       if (k < K && m < M) {
         uint16_t h, l;
-        split_bf16(tile[tx][cc], h, l);
+        split2(fmt, tile[tx][cc], h, l);
         hi_t[k * pitch_t + m] = h;
         if (MIXED && lo_t != nullptr) lo_t[k * pitch_t + m] = l;
       }
@@ -914,8 +973,22 @@ int atq_route_mask_mul(int device, const float* x, const float* grad_out, const 
   return ATQ_OK;
 }
 
+int atq_absmax_scale(int device, const float* x, int64_t rows, int64_t cols, int64_t ld, float bound_mul, const float* extra,
+                     float* slot, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && slot && rows > 0 && cols > 0 && ld >= cols, "null pointer, empty shape or ld < cols");
+  ATQ_CHECK_ARG(bound_mul > 0.f, "bound_mul must be positive");
+  ATQ_ENSURE_DEVICE(device);
+  const int vec = (ld == cols && aligned16(x)) ? 1 : 0;
+  const int64_t n = rows * cols;
+  int grid = vec ? stream_grid(device, (n >> 2) + 1, kThreads * 4, 4)
+                 : (int)(rows < (int64_t)sm_count(device) * 4 ? rows : (int64_t)sm_count(device) * 4);
+  absmax_scale_kernel<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(x, rows, cols, ld, bound_mul, extra, slot, vec);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
 int atq_split_bf16(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in, uint16_t* hi, uint16_t* lo,
-                   int64_t pitch, atq_stream_t stream_) {
+                   int64_t pitch, const float* scale_slot, atq_stream_t stream_) {
   ATQ_CHECK_ARG(x && hi && rows > 0 && cols > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG(ld_in >= cols && pitch >= cols && (pitch % 8) == 0, "need ld_in >= cols, pitch >= cols, pitch % 8 == 0");
   ATQ_ENSURE_DEVICE(device);
@@ -923,19 +996,19 @@ int atq_split_bf16(int device, const float* x, int64_t rows, int64_t cols, int64
   if (ld_in == cols && pitch == cols && aligned16(x) && aligned16(hi) && (lo == nullptr || aligned16(lo))) {
     int64_t n = rows * cols;
     int grid = stream_grid(device, n >> 2, kThreads * kUnroll, 8);
-    if (lo) split_flat_kernel<true><<<grid, kThreads, 0, stream>>>(x, n, hi, lo);
-    else split_flat_kernel<false><<<grid, kThreads, 0, stream>>>(x, n, hi, lo);
+    if (lo) split_flat_kernel<true><<<grid, kThreads, 0, stream>>>(x, n, hi, lo, scale_slot);
+    else split_flat_kernel<false><<<grid, kThreads, 0, stream>>>(x, n, hi, lo, scale_slot);
   } else {
     int grid = (int)(rows < (int64_t)sm_count(device) * 8 ? rows : (int64_t)sm_count(device) * 8);
-    if (lo) split_rows_kernel<true><<<grid, kThreads, 0, stream>>>(x, rows, cols, ld_in, hi, lo, pitch);
-    else split_rows_kernel<false><<<grid, kThreads, 0, stream>>>(x, rows, cols, ld_in, hi, lo, pitch);
+    if (lo) split_rows_kernel<true><<<grid, kThreads, 0, stream>>>(x, rows, cols, ld_in, hi, lo, pitch, scale_slot);
+    else split_rows_kernel<false><<<grid, kThreads, 0, stream>>>(x, rows, cols, ld_in, hi, lo, pitch, scale_slot);
   }
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }
 
 int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in, uint16_t* hi_t,
-                     uint16_t* lo_t, int64_t pitch_t, float* colsum, atq_stream_t stream_) {
+                     uint16_t* lo_t, int64_t pitch_t, float* colsum, const float* scale_slot, atq_stream_t stream_) {
   ATQ_CHECK_ARG(x && hi_t && rows > 0 && cols > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG(ld_in >= cols && pitch_t >= rows && (pitch_t % 8) == 0, "need ld_in >= cols, pitch_t >= rows, pitch_t % 8 == 0");
   ATQ_CHECK_ARG(colsum == nullptr, "fused colsum not supported in this build; use atq_colsum_f32");
@@ -943,15 +1016,15 @@ int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int
   cudaStream_t stream = (cudaStream_t)stream_;
   dim3 grid((unsigned)((cols + kTile - 1) / kTile), (unsigned)((rows + kTile - 1) / kTile));
   ATQ_CHECK_ARG(grid.y <= 65535u, "rows too large for one launch");
-  if (lo_t) split_t_kernel<true><<<grid, 256, 0, stream>>>(x, rows, cols, ld_in, hi_t, lo_t, pitch_t);
-  else split_t_kernel<false><<<grid, 256, 0, stream>>>(x, rows, cols, ld_in, hi_t, lo_t, pitch_t);
+  if (lo_t) split_t_kernel<true><<<grid, 256, 0, stream>>>(x, rows, cols, ld_in, hi_t, lo_t, pitch_t, scale_slot);
+  else split_t_kernel<false><<<grid, 256, 0, stream>>>(x, rows, cols, ld_in, hi_t, lo_t, pitch_t, scale_slot);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }
 
 int atq_build_ternary_operands(int device, const float* w, int64_t M, int64_t K, const float* thr, uint8_t* packed,
                                uint8_t* packed_t, uint16_t* tb, int64_t pitch, uint16_t* tb_t, int64_t pitch_t,
-                               void* stats, atq_stream_t stream_) {
+                               void* stats, int fp16, atq_stream_t stream_) {
   ATQ_CHECK_ARG(w && thr && M > 0 && K > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG(packed == nullptr || (K % 4) == 0, "packed output needs K % 4 == 0 (use atq_ternarize_pack2)");
   ATQ_CHECK_ARG(packed_t == nullptr || (M % 4) == 0, "packed_t output needs M % 4 == 0");
@@ -961,14 +1034,14 @@ int atq_build_ternary_operands(int device, const float* w, int64_t M, int64_t K,
   dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((M + kTile - 1) / kTile));
   ATQ_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
   build_operands_kernel<false><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, nullptr, M, K, thr, nullptr, packed, packed_t, tb, nullptr,
-                                                                         pitch, tb_t, nullptr, pitch_t, (TernStats*)stats);
+                                                                         pitch, tb_t, nullptr, pitch_t, (TernStats*)stats, nullptr, fp16);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }
 
 int atq_build_mixed_operands(int device, const float* w, const float* mask, int64_t M, int64_t K, const float* thr,
                              const float* alpha, uint8_t* packed, uint16_t* hi, uint16_t* lo, int64_t pitch,
-                             uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, atq_stream_t stream_) {
+                             uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, const float* scale_slot, atq_stream_t stream_) {
   ATQ_CHECK_ARG(w && mask && thr && alpha && M > 0 && K > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG(packed == nullptr || (K % 4) == 0, "packed output needs K % 4 == 0 (use atq_ternarize_pack2)");
   ATQ_CHECK_ARG(hi == nullptr || (pitch >= K && pitch % 8 == 0), "bad pitch");
@@ -977,7 +1050,7 @@ int atq_build_mixed_operands(int device, const float* w, const float* mask, int6
   dim3 grid((unsigned)((K + kTile - 1) / kTile), (unsigned)((M + kTile - 1) / kTile));
   ATQ_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
   build_operands_kernel<true><<<grid, 256, 0, (cudaStream_t)stream_>>>(w, mask, M, K, thr, alpha, packed, nullptr, hi, lo, pitch, hi_t,
-                                                                        lo_t, pitch_t, nullptr);
+                                                                        lo_t, pitch_t, nullptr, scale_slot, 0);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }
@@ -1002,7 +1075,7 @@ size_t atq_workspace_bytes_split_colsum(int64_t rows, int64_t cols) {
 }
 
 int atq_split_bf16_colsum(int device, const float* x, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo,
-                          float* colsum_out, void* ws, size_t ws_bytes, atq_stream_t stream_) {
+                          float* colsum_out, void* ws, size_t ws_bytes, const float* scale_slot, atq_stream_t stream_) {
   ATQ_CHECK_ARG(x && hi && colsum_out && rows > 0 && cols > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG((cols % 8) == 0 && aligned16(x) && aligned16(hi) && (lo == nullptr || aligned16(lo)),
                 "needs cols % 8 == 0 and 16-byte aligned contiguous tensors");
@@ -1015,8 +1088,8 @@ int atq_split_bf16_colsum(int device, const float* x, int64_t rows, int64_t cols
   cudaStream_t stream = (cudaStream_t)stream_;
   const int64_t threads = (cols >> 2) * R;
   const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
-  if (lo) split_colsum_kernel<true><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R);
-  else split_colsum_kernel<false><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R);
+  if (lo) split_colsum_kernel<true><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R, scale_slot);
+  else split_colsum_kernel<false><<<grid, kThreads, 0, stream>>>(x, rows, cols, hi, lo, (float*)ws, R, scale_slot);
   ATQ_LAUNCH_CHECK();
   colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>((const float*)ws, R, cols, colsum_out);
   ATQ_LAUNCH_CHECK();
@@ -1024,7 +1097,7 @@ int atq_split_bf16_colsum(int device, const float* x, int64_t rows, int64_t cols
 }
 
 int atq_gelu_dropout_split(int device, const float* y, int64_t rows, int64_t cols, float dropout_p,
-                           const unsigned long long* seed, uint16_t* hi, uint16_t* lo, atq_stream_t stream_) {
+                           const unsigned long long* seed, uint16_t* hi, uint16_t* lo, const float* scale_slot, atq_stream_t stream_) {
   ATQ_CHECK_ARG(y && hi && rows > 0 && cols > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG((cols % 8) == 0 && aligned16(y) && aligned16(hi) && (lo == nullptr || aligned16(lo)),
                 "needs cols % 8 == 0 and 16-byte aligned contiguous tensors");
@@ -1037,15 +1110,15 @@ int atq_gelu_dropout_split(int device, const float* y, int64_t rows, int64_t col
   const int64_t threads = (cols >> 2) * R;
   const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (lo) act_split_kernel<false, true><<<grid, kThreads, 0, stream>>>(y, nullptr, rows, cols, hi, lo, nullptr, R, ap);
-  else act_split_kernel<false, false><<<grid, kThreads, 0, stream>>>(y, nullptr, rows, cols, hi, lo, nullptr, R, ap);
+  if (lo) act_split_kernel<false, true><<<grid, kThreads, 0, stream>>>(y, nullptr, rows, cols, hi, lo, nullptr, R, ap, scale_slot);
+  else act_split_kernel<false, false><<<grid, kThreads, 0, stream>>>(y, nullptr, rows, cols, hi, lo, nullptr, R, ap, scale_slot);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }
 
 int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y, int64_t rows, int64_t cols, float dropout_p,
                                       const unsigned long long* seed, uint16_t* hi, uint16_t* lo, float* colsum_out,
-                                      void* ws, size_t ws_bytes, atq_stream_t stream_) {
+                                      void* ws, size_t ws_bytes, const float* scale_slot, atq_stream_t stream_) {
   ATQ_CHECK_ARG(g && y && hi && colsum_out && rows > 0 && cols > 0, "null pointer or empty shape");
   ATQ_CHECK_ARG((cols % 8) == 0 && aligned16(g) && aligned16(y) && aligned16(hi) && (lo == nullptr || aligned16(lo)),
                 "needs cols % 8 == 0 and 16-byte aligned contiguous tensors");
@@ -1062,8 +1135,8 @@ int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y
   const int64_t threads = (cols >> 2) * R;
   const unsigned grid = (unsigned)((threads + kThreads - 1) / kThreads);
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (lo) act_split_kernel<true, true><<<grid, kThreads, 0, stream>>>(g, y, rows, cols, hi, lo, (float*)ws, R, ap);
-  else act_split_kernel<true, false><<<grid, kThreads, 0, stream>>>(g, y, rows, cols, hi, lo, (float*)ws, R, ap);
+  if (lo) act_split_kernel<true, true><<<grid, kThreads, 0, stream>>>(g, y, rows, cols, hi, lo, (float*)ws, R, ap, scale_slot);
+  else act_split_kernel<true, false><<<grid, kThreads, 0, stream>>>(g, y, rows, cols, hi, lo, (float*)ws, R, ap, scale_slot);
   ATQ_LAUNCH_CHECK();
   colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>((const float*)ws, R, cols, colsum_out);
   ATQ_LAUNCH_CHECK();

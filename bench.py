@@ -1,23 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- multimodal ATQ training throughput on B200 (BASELINE.json metric), with the
-roofline of the dominant hot-path kernel and the reference algorithm's CPU path timed beside it.
+"""bench.py -- multimodal ATQ training throughput on B200 (BASELINE.json metric), with the roofline of the
+dominant hot-path kernel and the REFERENCE'S OWN CPU path timed beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload flickr8k|vitb16] [--mode parity|fast]
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
-A "step" is one optimisation step of the named synthetic config (forward through every ternary
-layer, contrastive loss, backward, gradient all-reduce when N > 1, AdamW).
-  value : whole-job samples/s with the batch already resident in HBM
-  e2e   : the same step with the batch copied from pinned host memory and the loss read back
-  roofline / rooflines : CUDA-event timings of this library's kernels (in the step, and at the
-          BASELINE config-3 / config-5 shapes) against MEASURED_PEAKS.json
-  cpu_baseline / --impl reference : the CPU port of the reference algorithm (oracle/) on the same
-          config, on the box's host cores.
+A "step" is one optimisation step of the named synthetic config (re-quantization of every ternary layer the
+optimizer touched, forward, contrastive loss, backward, gradient all-reduce when N > 1, AdamW).
+
+  value            whole-job samples/s with the batch already resident in HBM (BASELINE config 2, the headline)
+  e2e              the same step with the batch copied from pinned host memory and the loss read back
+  roofline         dominant own kernel inside the headline step (CUDA events around every C-ABI call)
+  cpu_baseline     `--impl reference` run on the host cores: the UNMODIFIED reference (oracle/_ref: its own atq, models
+                   and loss) on the same config; falls back to the CPU port only if the staged copy is missing
+  dropin           the reference's own models bound to THIS repo's atq, eager, torch.optim.AdamW: nothing but the
+                   reference's five public names is used -- the cost of staying strictly behind the boundary
+  configs.vitb16   BASELINE config 4 (ViT-B/16-sized + 12-layer text tower, 512 samples per GPU) on the same build
+  rooflines        own kernels at BASELINE config-3 (GEMM) / config-5 (quantize, pack) shapes, timed alone
+  summary          the figures BASELINE's metric names, compact, LAST in the line
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import dataclasses
 import json
 import os
 import statistics
@@ -27,7 +34,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "atq-multimodal_b200")):
+PKG_DIR = os.path.join(ROOT, "atq-multimodal_b200")
+for _p in (ROOT, PKG_DIR):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -36,6 +44,7 @@ import torch  # noqa: E402
 METRIC = "multimodal ATQ train samples/sec"
 UNIT = "samples/s"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+L2_NOTE = "flushed between timed steps (256 MB write, outside the per-step events)"
 
 
 def load_peaks():
@@ -48,6 +57,12 @@ def load_peaks():
     d = dict(FALLBACK_PEAKS)
     d["_source"] = "fallback"
     return d
+
+
+def shared_config(cfg, n_gpus):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": cfg.name, "per_gpu_batch": cfg.batch, "global_batch": cfg.batch * n_gpus,
+            "parallelism": f"dp{n_gpus}", "l2": L2_NOTE}
 
 
 # ---------------------------------------------------------------------------------------
@@ -151,25 +166,76 @@ def timed_steps(step_fn, steps, flush, world):
 
 
 # ---------------------------------------------------------------------------------------
-# CPU port of the reference (oracle) on the same config
+# reference arm: the unmodified reference (oracle/_ref) on the host cores
 # ---------------------------------------------------------------------------------------
-def cpu_port_throughput(cfg, steps, warmup):
-    from oracle import policy as P
-    from workloads import models as M
+def reference_throughput(cfg, steps, warmup):
+    """-> (samples/s, s/step, kind, description).  kind "reference": the reference's own atq + models + loss + scheduler
+    (staged copy, oracle/install_ref.py) driven exactly like train_multimodal.py; kind "port": the oracle restatement
+    (only when the staged copy is missing, or for the ViT-sized config the reference has no model for)."""
+    from oracle import ref_env
     from workloads import train as T
     torch.set_num_threads(os.cpu_count() or 1)
-    model, _, manager = T.build_retrieval(M.oracle_layers(), cfg)
-    P.scheduler_step(model, cfg.epoch, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs)
-    opt = T.make_optimizer(model, cfg)
     batches = T.synthetic_batches(cfg, 2, seed=42)
-    model.train()
+    if cfg.image_tower == "resnet18" and ref_env.available():
+        ref_env.activate("reference")
+        from oracle import ref_tasks as R
+        with contextlib.redirect_stdout(sys.stderr):  # the reference's constructors print
+            model = R.build_retrieval(cfg.vocab, cfg.embed_dim, cfg.hidden_dim, seed=42)
+            R.step_schedule(model, cfg.epoch, cfg.total_epochs, cfg.warmup_epochs)
+        _, manager = R.build_loss(model, cfg.epoch, cfg.total_epochs)
+        opt = R.make_optimizer(model, cfg.lr)
+        model.train()
+        step = lambda b: R.retrieval_step(model, manager, opt, b)  # noqa: E731
+        kind = "reference"
+        what = ("the unmodified reference (oracle/_ref: its atq, models.ATQMultimodalRetrieval, HardNegativeMiningInfoNCE, "
+                "GradualQuantizationScheduler) stepped as train_multimodal.py:540-585 does")
+    else:
+        from oracle import policy as P
+        from workloads import models as M
+        model, _, manager = T.build_retrieval(M.oracle_layers(), cfg)
+        P.scheduler_step(model, cfg.epoch, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs)
+        opt = T.make_optimizer(model, cfg)
+        model.train()
+        step = lambda b: T.retrieval_step(model, manager, opt, b)  # noqa: E731
+        kind = "port"
+        what = "the CPU port of the reference algorithm (oracle/ layers in the harness model)"
     for i in range(warmup):
-        float(T.retrieval_step(model, manager, opt, batches[i % 2]).detach())
+        float(step(batches[i % 2]).detach())
     t0 = time.perf_counter()
     for i in range(steps):
-        float(T.retrieval_step(model, manager, opt, batches[i % 2]).detach())
+        float(step(batches[i % 2]).detach())
     dt = time.perf_counter() - t0
-    return cfg.batch * steps / dt, dt / steps
+    return cfg.batch * steps / dt, dt / steps, kind, what
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, s_per_step, kind, what = reference_throughput(cfg, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(s_per_step * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": shared_config(cfg, args.gpus),
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{args.steps} full optimisation steps (batch {cfg.batch}) of {what}; torch CPU, {cores} threads"},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args, workload):
+    """The reference arm in a process of its own (it binds the name `atq` to the reference's package)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(args.cpu_steps), "--warmup", "1",
+           "--workload", workload]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["CUDA_VISIBLE_DEVICES"] = ""
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        return line["cpu_baseline"]
+    except Exception as exc:  # the baseline is a reported number, not a reason to lose the GPU line
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": f"failed: {exc!r}"[:200]}
 
 
 # ---------------------------------------------------------------------------------------
@@ -191,95 +257,166 @@ def _event_time(fn, iters, flush=None):
     return total / iters  # ms
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures
-# (profiles/r01_ncu_full_tgemm_v2.csv, profiles/r01_ncu_full_streaming_v2.csv); same shapes as below
-NCU_TRAFFIC = {
-    "tgemm parity tma": 255.7e6 + 109.8e6,
-    "tgemm parity packed": 138.8e6 + 92.0e6,
-    "select 4096": 3 * 67.1e6 + 1.5e6,
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {}
+try:
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
+        NCU_TRAFFIC = json.load(_f)
+except Exception:
+    pass
 
 
-def kernel_rooflines(device, peaks, flush, quick=True):
-    """BASELINE config 3 (GEMM, tensor-bound) and config 5 (quantize/pack, HBM-bound) shapes."""
+def gemm_rooflines(device, peaks, flush):
+    """BASELINE config 3: TernaryLinear / RPB at 4096^2 and 8192^2 weights, 8192 tokens; forward GEMM alone and the
+    whole layer forward+backward (operand splits, bias / alpha reductions included; weights quantized once, H7)."""
+    import atq
     import atq._engine as eng
     out = []
-    hbm, tf = peaks["hbm_gbs"], peaks["bf16_tflops"]
-    src = "of measured" if peaks["_source"] == "measured" else "of fallback"
-    # ---- config 3: TernaryLinear forward GEMM, 4096x4096 packed weights, 8192 tokens
-    M = K = 4096
+    tf = peaks["bf16_tflops"]
+    src = "measured" if peaks["_source"] == "measured" else "fallback"
+    prev = atq.get_gemm_mode()
     N = 8192
-    g = torch.Generator(device=device).manual_seed(0)
-    w = (torch.rand(M, K, device=device, generator=g) * 2 - 1) / K ** 0.5
-    x = torch.randn(N, K, device=device, generator=g)
-    thr = eng.adaptive_threshold(w, 0.3)
-    tb = torch.empty((M, K), dtype=torch.bfloat16, device=device)
-    tbt = torch.empty((K, M), dtype=torch.bfloat16, device=device)
-    import atq._native as nv
-    packed = torch.empty(M * K // 4, dtype=torch.uint8, device=device)
-    nv.call("atq_build_ternary_operands", 0 if device.index is None else device.index, w.data_ptr(), M, K, thr.data_ptr(),
-            packed.data_ptr(), None, tb.data_ptr(), K, tbt.data_ptr(), M, None, nv.stream_ptr(device.index or 0))
-    for mode, want_lo in (("parity(hi+lo)", True), ("fast(bf16)", False)):
-        xa = eng.split_bf16(x, want_lo)
-        for bsrc, fn in (("B = 2-bit packed, unpacked in smem", lambda: eng.tgemm_packed(xa, packed, N, M, K)),
-                         ("B = bf16 via TMA", lambda: eng.tgemm(xa, (tb, None, K), N, M, K))):
-            ms = _event_time(fn, 5, flush)
-            ach = 2.0 * N * M * K / (ms * 1e-3) / 1e12
-            traffic = NCU_TRAFFIC.get("tgemm parity " + ("packed" if "packed" in bsrc else "tma")) if want_lo else None
-            out.append({"kernel": f"tgemm_kernel fwd {mode}, {bsrc}", "workload": f"config3 TernaryLinear {M}x{K}, {N} tokens",
-                        "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
-                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": traffic,
-                        "algorithmic_bytes": 2 * N * K * (2 if want_lo else 1) + (M * K // 4 if "packed" in bsrc else 2 * M * K) + 4 * N * M})
-    # ---- config 4: fused attention core at the image-tower shape (512 images x 12 heads x 197 tokens, head_dim 64)
+    for size in (4096, 8192):
+        for kind, ratio in (("TernaryLinear", None), ("RPB0.2", 0.2)):
+            torch.manual_seed(0)
+            mod = (atq.TernaryLinear(size, size) if ratio is None else
+                   atq.ResidualPrecisionBoostLinear(size, size, ratio, True, 0.3)).to(device)
+            x = torch.randn(N, size, device=device)
+            gy = torch.randn(N, size, device=device)
+            xi = x.clone().requires_grad_(True)
+            for mode in ("fast", "parity"):
+                atq.set_gemm_mode(mode)
+                mod._ops.key = None
+                with torch.no_grad():
+                    mod(x[:8])
+
+                def fwd():
+                    with torch.no_grad():
+                        mod(x)
+
+                def fwdbwd():
+                    mod.zero_grad(set_to_none=True)
+                    xi.grad = None
+                    mod(xi).backward(gy)
+
+                ms_f = _event_time(fwd, 4, flush)
+                ms_fb = _event_time(fwdbwd, 4, flush)
+                n_gemm = 2 if ratio is None else 3
+                fl = 2.0 * N * size * size
+                key = f"{kind} {size} {mode}"
+                out.append({"kernel": "tgemm_kernel (+ operand split)", "workload": f"config3 {kind} {size}x{size}, {N} tokens, {mode}",
+                            "bound": "tensor", "unit": "TFLOP/s", "peak": tf, "peak_kind": f"bf16 burst {src}",
+                            "fwd_ms": round(ms_f, 4), "fwd_achieved": round(fl / ms_f / 1e9, 1), "fwd_frac": round(fl / ms_f / 1e9 / tf, 4),
+                            "fwdbwd_ms": round(ms_fb, 4), "achieved": round(n_gemm * fl / ms_fb / 1e9, 1),
+                            "frac": round(n_gemm * fl / ms_fb / 1e9 / tf, 4), "traffic": NCU_TRAFFIC.get(key),
+                            "useful_flops": f"{n_gemm} GEMMs x 2*N*K*M (hi/lo terms count 0)"})
+            del mod, x, gy, xi
+            torch.cuda.empty_cache()
+    atq.set_gemm_mode(prev)
+    return out
+
+
+def attention_rooflines(device, peaks, flush):
     import atq
     from atq import attention as A
+    out = []
+    tf = peaks["bf16_tflops"]
+    src = "measured" if peaks["_source"] == "measured" else "fallback"
+    g = torch.Generator(device=device).manual_seed(0)
     b_, h_, l_ = 512, 12, 197
     q, k, v = (torch.randn(b_, l_, h_ * 64, device=device, generator=g).requires_grad_(True) for _ in range(3))
     dout = torch.randn(b_, l_, h_ * 64, device=device, generator=g)
     seed = torch.tensor([1], dtype=torch.int64, device=device)
     prev_mode = atq.get_gemm_mode()
-    for mode in ("parity", "fast"):
+    for mode in ("fast", "parity"):
         atq.set_gemm_mode(mode)
         with torch.no_grad():
-            ms_f = _event_time(lambda: A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed), 5, flush)
+            ms_f = _event_time(lambda: A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed), 4, flush)
         o = A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed)
 
         def bwd():
             q.grad = k.grad = v.grad = None
             o.backward(dout, retain_graph=True)
-        ms_b = _event_time(bwd, 5, flush)
+        ms_b = _event_time(bwd, 4, flush)
         for name, ms, fl in (("attention_fwd_kernel", ms_f, 4.0), ("attention_bwd_kernel", ms_b, 10.0)):
             ach = fl * l_ * l_ * 64 * b_ * h_ / (ms * 1e-3) / 1e12
             out.append({"kernel": f"{name} {mode}", "workload": f"config4 attention core {b_}x{h_}x{l_}x64, dropout 0.1",
                         "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
-                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None,
-                        "note": "useful flops 4 (fwd) / 10 (bwd) x L^2 x 64 per head; softmax-issue / phase-latency bound, not tensor bound"})
+                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None})
         del o
     atq.set_gemm_mode(prev_mode)
-    del q, k, v, dout
-    # ---- config 5: quantize + pack, one 4096x4096 layer (64 MiB fp32; L2 flushed between runs)
+    return out
+
+
+def streaming_rooflines(device, peaks, flush):
+    """BASELINE config 5: one 4096x4096 layer, and the 1 B-weight layer list (60 layers, mixed-precision per-layer
+    sparsities from MixedPrecisionATQ), thresholds batched."""
+    import atq._engine as eng
+    from atq.mixed_precision_atq import MixedPrecisionATQ
+    out = []
+    hbm = peaks["hbm_gbs"]
+    src = "measured" if peaks["_source"] == "measured" else "fallback"
+
+    def rec(kernel, workload, bpe, n, ms, traffic=None, note=None):
+        ach = bpe * n / (ms * 1e-3) / 1e9
+        r = {"kernel": kernel, "workload": workload, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
+             "frac": round(ach / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4), "alg_bytes_per_elem": bpe, "traffic": traffic}
+        if note:
+            r["note"] = note
+        out.append(r)
+
+    g = torch.Generator(device=device).manual_seed(0)
+    M = K = 4096
     n = M * K
-    ms = _event_time(lambda: eng.adaptive_threshold(w, 0.3), 5, flush)
-    out.append({"kernel": "select_pass_kernel x3 (exact k-th |W|)", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
-                "achieved": round(4.0 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(4.0 * n / (ms * 1e-3) / 1e9 / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4),
-                "traffic": NCU_TRAFFIC["select 4096"], "note": "4 B/elem over the whole 3-pass select (3 full reads: traffic = 3x algorithmic)"})
-    ms = _event_time(lambda: eng.ternarize_pack2(w, thr), 5, flush)
-    out.append({"kernel": "ternarize_kernel -> 2-bit", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
-                "achieved": round(4.25 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(4.25 * n / (ms * 1e-3) / 1e9 / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4), "traffic": None})
+    w = (torch.rand(M, K, device=device, generator=g) * 2 - 1) / K ** 0.5
+    thr = eng.adaptive_threshold(w, 0.3)
+    wl = f"config5 one layer {M}x{K}"
+    rec("select (exact k-th |W|)", wl, 4.0, n, _event_time(lambda: eng.adaptive_threshold(w, 0.3), 5, flush),
+        NCU_TRAFFIC.get("select 4096"), "4 B/elem over the whole select")
+    rec("ternarize_kernel -> 2-bit", wl, 4.25, n, _event_time(lambda: eng.ternarize_pack2(w, thr), 5, flush), NCU_TRAFFIC.get("ternarize_pack 4096"))
     packed = eng.ternarize_pack2(w, thr)
-    ms = _event_time(lambda: eng.unpack2(packed, n), 5, flush)
-    out.append({"kernel": "unpack2_kernel -> fp32", "workload": f"config5 layer {M}x{K}", "bound": "hbm",
-                "achieved": round(4.25 * n / (ms * 1e-3) / 1e9, 1), "peak": hbm, "unit": "GB/s",
-                "frac": round(4.25 * n / (ms * 1e-3) / 1e9 / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4), "traffic": None})
+    tern = eng.unpack2(packed, n)
+    rec("pack fp32 ternary -> 2-bit", wl, 4.25, n, _event_time(lambda: eng.pack2_from_f32(tern), 5, flush))
+    rec("unpack2_kernel -> fp32", wl, 4.25, n, _event_time(lambda: eng.unpack2(packed, n), 5, flush), NCU_TRAFFIC.get("unpack 4096"))
+    del w, packed, tern
+    # ---- 1 B weights
+    names = ["image_encoder.layers.{i}.self_attn.q_proj", "text_encoder.layers.{i}.linear1", "text_projector.{i}",
+             "encoder.ffn.intermediate.{i}", "image_encoder.layers.{i}.linear2", "text_encoder.attention_pool.{i}"]
+    shapes = [(4096, 4096)] * 59 + [(2464, 4096)]
+    ss = []
+    for i in range(len(shapes)):
+        nm = names[i % len(names)].format(i=i)
+        _, s = MixedPrecisionATQ.calculate_quantization_params(None, nm, (0, 5, 9)[i % 3], 10, 0.3 if "image" in nm else 0.2)
+        ss.append(s)
+    ws = [(torch.rand(m, k, device=device, generator=g) * 2 - 1) / k ** 0.5 for m, k in shapes]
+    total = sum(t.numel() for t in ws)
+    wl = f"config5 {total} weights in {len(ws)} layers, per-layer sparsity from MixedPrecisionATQ"
+
+    def quantize_pack():
+        th = eng.adaptive_threshold_batched(ws, ss)
+        return [eng.ternarize_pack2(t, th[i]) for i, t in enumerate(ws)]
+
+    packed = quantize_pack()
+    rec("threshold, batched over layers", wl, 4.0, total, _event_time(lambda: eng.adaptive_threshold_batched(ws, ss), 3, flush))
+    ms_qp = _event_time(quantize_pack, 3, flush)
+    rec("quantize+pack (threshold + ternarize -> 2-bit)", wl, 8.25, total, ms_qp, None,
+        "two-read bound 8.25 B/elem (one read for the order statistic, one for ternarize); single-read bound 4.25 -> "
+        f"{round(4.25 * total / (ms_qp * 1e-3) / 1e9 / hbm, 4)} of peak")
+    rec("unpack 2-bit -> fp32", wl, 4.25, total, _event_time(lambda: [eng.unpack2(p, t.numel()) for p, t in zip(packed, ws)], 3, flush))
+    tern = [eng.unpack2(p, t.numel()) for p, t in zip(packed, ws)]
+    del ws
+    rec("pack fp32 ternary -> 2-bit", wl, 4.25, total, _event_time(lambda: [eng.pack2_from_f32(t)[0] for t in tern], 3, flush))
+    out.append({"kernel": "quantize+pack throughput", "workload": wl, "gelem_per_s": round(total / ms_qp / 1e6, 1)})
+    del tern, packed
+    torch.cuda.empty_cache()
     return out
 
 
 class CallProfiler:
     """Brackets every C-ABI call with CUDA events (a separate, untimed pass of the same step)."""
 
-    FLOPS = {"atq_tgemm": lambda a: 2.0 * a[0] * a[1] * a[2], "atq_tgemm_dw_masked": lambda a: 2.0 * a[0] * a[1] * a[2]}
+    FLOPS = {"atq_tgemm": lambda a: 2.0 * a[0] * a[1] * a[2], "atq_tgemm_dw_masked": lambda a: 2.0 * a[0] * a[1] * a[2],
+             "atq_tgemm_packed": lambda a: 2.0 * a[0] * a[1] * a[2]}
 
     def __init__(self):
         self.records = []
@@ -296,8 +433,6 @@ class CallProfiler:
             self.records.append((name, tuple(a for a in args[1:4] if isinstance(a, int)), s, e))
 
         nv.call = wrapped
-        import atq._engine as eng
-        eng.nv.call = wrapped
         return self
 
     def __exit__(self, *exc):
@@ -316,52 +451,26 @@ class CallProfiler:
 
 
 # ---------------------------------------------------------------------------------------
-def run_reference(args, cfg):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    value, s_per_step = cpu_port_throughput(cfg, args.steps, args.warmup)
-    cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(s_per_step * 1e3, 2),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg.name, "per_gpu_batch": cfg.batch, "device": "cpu"},
-            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} full optimisation steps of the same config (batch {cfg.batch}) on "
-                                       f"the CPU port of the reference algorithm (oracle/, torch CPU, {cores} threads)"},
-            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
-
-
-def run_ours(args, cfg):
+# one workload on this repo's path
+# ---------------------------------------------------------------------------------------
+def measure_workload(args, cfg, steps, warmup, ctx, use_graph, clock_sampler=None):
+    """Builds the harness model of `cfg` on the B200 atq, runs W warm-up + K timed steps (resident batch), K e2e steps
+    (pinned host batch in, loss out), then an untimed profiling pass.  Returns the result dictionary."""
     import atq
     import atq._native as nv
     from atq import parallel
     from atq.mixed_precision_atq import GradualQuantizationScheduler
+    from atq.optim import FlatAdamW
     from workloads import train as T
 
-    rank, world, local = parallel.init_from_env()
-    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
-    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    device = torch.device("cuda", local)
-    torch.cuda.set_device(device)
-    atq.set_gemm_mode(args.mode)
-    peaks = load_peaks()
-
-    if args.serial_towers:
-        from workloads import models as WM
-        WM.PARALLEL_TOWERS = False
+    rank, world, device, peaks, flush = ctx["rank"], ctx["world"], ctx["device"], ctx["peaks"], ctx["flush"]
     model, _, manager = T.build_retrieval(atq, cfg)
     model.to(device).train()
     if cfg.image_tower == "resnet18":
-        # cuDNN's tensor-core convolutions are NHWC: keep the fp32 trunk channels-last so no
-        # NCHW<->NHWC transposes run around every convolution (caller-side layout, same maths)
+        # cuDNN's tensor-core convolutions are NHWC: keep the fp32 trunk channels-last so no NCHW<->NHWC transposes
+        # run around every convolution (caller-side layout, same maths)
         model.image_encoder.base_model.to(memory_format=torch.channels_last)
     GradualQuantizationScheduler(model, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs).step(cfg.epoch)
-    # the small-shape config is launch-bound and runs as one CUDA graph; the ViT-B-sized config is
-    # kernel-bound (and its activations would be held twice by a capture pool), so it runs eagerly
-    use_graph = (not args.no_graph) and args.workload == "flickr8k"
-    from atq.optim import FlatAdamW
     opt = T.make_optimizer(model, cfg, capturable=use_graph, fused=True, adamw_cls=None if args.torch_adamw else FlatAdamW)
     sync = None
     if world > 1:  # --sparse-grads: only the entries under each RPB precision_mask travel (SURVEY 8f rank 4)
@@ -374,16 +483,15 @@ def run_ours(args, cfg):
         host = [channels_last_images(b) for b in host]
     host = [tuple(t.pin_memory() for t in b) for b in host]
     resident = [to_device(b, device) for b in host]
-    flush = L2Flusher(device)
     losses = []
 
     def eager_step(batch):
         return T.retrieval_step(model, manager, opt, batch, gather, sync, atq.prepare_quantization)
 
-    sampler = ClockSampler(local)
-    sampler.start()  # samples from warm-up to the end of the e2e leg: the GPU is under load throughout
+    if clock_sampler is not None:
+        clock_sampler.start()  # samples from warm-up to the end of the e2e leg: the GPU is under load throughout
     run_step = eager_step
-    for i in range(args.warmup):
+    for i in range(warmup):
         eager_step(resident[i % pool])
     torch.cuda.synchronize()
     gstep = None
@@ -406,87 +514,189 @@ def run_ours(args, cfg):
         losses.append(float(loss.detach()))       # device -> host read of the step's loss
 
     k0 = nv.kernel_launch_count()
-    ms_total = timed_steps(step_resident, args.steps, flush, world)
+    ms_total = timed_steps(step_resident, steps, flush, world)
     launches = nv.kernel_launch_count() - k0
     if gstep is not None:
-        launches = gstep.own_kernels_per_replay * args.steps  # replays re-launch the captured kernels
+        launches = gstep.own_kernels_per_replay * steps  # replays re-launch the captured kernels
     ms_total = max_over_ranks(ms_total, device, world)
     step_e2e(0)
-    ms_e2e = max_over_ranks(timed_steps(step_e2e, args.steps, flush, world), device, world)
-    clocks = sampler.stop()
+    ms_e2e = max_over_ranks(timed_steps(step_e2e, steps, flush, world), device, world)
+    sustained = None
+    if args.sustained_steps > 0 and gstep is not None:
+        ms_long = max_over_ranks(timed_steps(step_resident, args.sustained_steps, lambda: None, world), device, world)
+        sustained = {"steps": args.sustained_steps, "value": round(cfg.batch * world * args.sustained_steps / (ms_long * 1e-3), 2),
+                     "unit": UNIT, "timed_region_s": round(ms_long * 1e-3, 3), "l2": "not flushed (back-to-back replays)"}
+    clocks = clock_sampler.stop() if clock_sampler is not None else None
 
     global_batch = cfg.batch * world
-    value = global_batch * args.steps / (ms_total * 1e-3)
-    e2e_value = global_batch * args.steps / (ms_e2e * 1e-3)
-    h2d = sum(t.numel() * t.element_size() for t in host[0])
-    final_loss = float(losses[-1]) if losses else float("nan")
+    res = {"value": round(global_batch * steps / (ms_total * 1e-3), 2), "unit": UNIT, "steps": steps, "warmup": warmup,
+           "ms_per_step": round(ms_total / steps, 4),
+           "e2e": {"value": round(global_batch * steps / (ms_e2e * 1e-3), 2), "unit": UNIT,
+                   "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host[0]), "d2h_bytes_per_step": 4,
+                   "ms_per_step": round(ms_e2e / steps, 4)},
+           "gpu_launches": int(launches), "clocks": clocks, "final_loss": round(float(losses[-1]), 5) if losses else None,
+           "execution": (("whole step captured in one CUDA graph" + ("" if args.serial_towers or cfg.image_tower != "resnet18" else
+                                                                      ", image / text towers on two streams (concurrent graph branches)"))
+                         if use_graph else "eager"),
+           "sustained": sustained}
 
-    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": cfg.name, "per_gpu_batch": cfg.batch, "global_batch": global_batch,
-                       "parallelism": f"dp{world}", "gemm_mode": args.mode,
-                       "gemm_arithmetic": "bf16 hi+lo operand pairs, fp32 TMEM accumulate" if args.mode == "parity"
-                       else "bf16 operands, fp32 TMEM accumulate",
-                       "quant_schedule": f"GradualQuantizationScheduler epoch {cfg.epoch}/{cfg.total_epochs}",
-                       "execution": ("whole step captured in one CUDA graph" + ("" if args.serial_towers or cfg.image_tower != "resnet18" else
-                                                                                 ", image / text towers on two streams (concurrent graph branches)"))
-                       if use_graph else "eager",
-                       "l2": "flushed between timed steps (256 MB write, outside the per-step events)"},
-            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": round(ms_e2e / args.steps, 4)},
-            "gpu_launches": int(launches), "clocks": clocks, "final_loss": round(final_loss, 5)}
-
-    # ---- roofline of the dominant kernel of THIS library inside the step (separate untimed pass;
-    # every rank runs it because the step contains collectives, rank 0 reports)
+    # ---- roofline of the dominant kernel of THIS library inside the step (separate untimed pass; every rank runs it
+    # because the step contains collectives, rank 0 reports)
     if gstep is not None:
         gstep.release()
     prof = CallProfiler()
     with prof:
         for i in range(2):
             eager_step(resident[i % pool])
+    summ = prof.summary()
+    own_ms = sum(d["ms"] for d in summ.values()) / 2
+    tf_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    src = "measured" if peaks["_source"] == "measured" else "fallback"
+    gemm_ms = sum(d["ms"] for n, d in summ.items() if d["flops"] > 0) / 2
+    gemm_fl = sum(d["flops"] for n, d in summ.items() if d["flops"] > 0) / 2
+    top = max(summ.items(), key=lambda kv: kv[1]["ms"]) if summ else None
+    if top is not None:
+        name, d = top
+        if d["flops"] > 0:
+            ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
+            res["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": tf_peak, "unit": "TFLOP/s",
+                               "frac": round(ach / tf_peak, 5), "traffic": None, "peak_kind": f"bf16 sustained {src}",
+                               "calls_per_step": d["calls"] // 2, "ms_per_step": round(d["ms"] / 2, 4),
+                               "share_of_own_kernel_time": round(d["ms"] / 2 / max(own_ms, 1e-9), 3),
+                               "note": "useful flops 2*rows*cols*k per call, CUDA events around each call of an eager pass"}
+        else:
+            res["roofline"] = {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": None, "traffic": None, "ms_per_step": round(d["ms"] / 2, 4)}
+    if gemm_ms > 0:
+        res["gemm_in_step"] = {"useful_tflops": round(gemm_fl / (gemm_ms * 1e-3) / 1e12, 2),
+                               "frac_of_sustained_peak": round(gemm_fl / (gemm_ms * 1e-3) / 1e12 / tf_peak, 4),
+                               "ms_per_step": round(gemm_ms, 3), "share_of_step": round(gemm_ms / (ms_total / steps), 3)}
+    res["own_kernel_ms_per_step"] = round(own_ms, 4)
+    res["own_calls"] = {k: {"calls_per_step": v["calls"] // 2, "ms_per_step": round(v["ms"] / 2, 4)} for k, v in
+                        sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+    # release everything this workload holds (the next one needs the memory)
+    if gstep is not None:
+        gstep.graph.reset()
+    del gstep, model, opt, sync, resident, host, manager
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def measure_dropin(args, cfg, steps, warmup, ctx):
+    """The reference's OWN model / loss / scheduler / step (oracle/_ref models + utils) bound to this repo's atq:
+    eager, torch.optim.AdamW, no prepare_quantization, no fused FFN / attention / residual, no CUDA graph."""
+    from oracle import ref_env
+    if not ref_env.available():
+        return {"unavailable": "oracle/_ref not staged"}
+    ref_env.activate("b200")
+    from oracle import ref_tasks as R
+    from workloads import train as T
+    device, flush = ctx["device"], ctx["flush"]
+    with contextlib.redirect_stdout(sys.stderr):
+        model = R.build_retrieval(cfg.vocab, cfg.embed_dim, cfg.hidden_dim, seed=42)
+        R.step_schedule(model, cfg.epoch, cfg.total_epochs, cfg.warmup_epochs)
+    model.to(device).train()
+    _, manager = R.build_loss(model, cfg.epoch, cfg.total_epochs)
+    opt = R.make_optimizer(model, cfg.lr)
+    host = [tuple(t.pin_memory() for t in b) for b in T.synthetic_batches(cfg, 4, seed=42)]
+    resident = [to_device(b, device) for b in host]
+    for i in range(warmup):
+        R.retrieval_step(model, manager, opt, resident[i % 4])
+    ms = timed_steps(lambda i: R.retrieval_step(model, manager, opt, resident[i % 4]), steps, flush, 1)
+    ms_e2e = timed_steps(lambda i: float(R.retrieval_step(model, manager, opt, to_device(host[i % 4], device)).detach()), steps, flush, 1)
+    out = {"value": round(cfg.batch * steps / (ms * 1e-3), 2), "unit": UNIT, "ms_per_step": round(ms / steps, 4),
+           "e2e": round(cfg.batch * steps / (ms_e2e * 1e-3), 2),
+           "what": "reference models.ATQMultimodalRetrieval + HardNegativeMiningInfoNCE + train_multimodal.py step, unmodified, on this atq (eager)"}
+    del model, opt, resident, host
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args, cfg):
+    import atq
+    from atq import parallel
+    from workloads import train as T
+
+    rank, world, local = parallel.init_from_env()
+    assert torch.cuda.is_available(), "bench.py (impl ours) needs a CUDA device; there is no CPU fallback"
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    atq.set_gemm_mode(args.mode)
+    if args.serial_towers:
+        from workloads import models as WM
+        WM.PARALLEL_TOWERS = False
+    ctx = {"rank": rank, "world": world, "device": device, "peaks": load_peaks(), "flush": L2Flusher(device)}
+    peaks = ctx["peaks"]
+
+    # the small-shape config is launch-bound and runs as one CUDA graph; the ViT-B-sized config is kernel-bound (and
+    # its activations would be held twice by a capture pool), so it runs eagerly
+    use_graph = (not args.no_graph) and cfg.image_tower == "resnet18"
+    head = measure_workload(args, cfg, args.steps, args.warmup, ctx, use_graph, ClockSampler(local))
+
+    line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": shared_config(cfg, world),
+            "arm": {"gemm_mode": args.mode,
+                    "gemm_arithmetic": "bf16 hi+lo operand pairs, fp32 TMEM accumulate" if args.mode == "parity" else "bf16 operands, fp32 TMEM accumulate",
+                    "quant_schedule": f"GradualQuantizationScheduler epoch {cfg.epoch}/{cfg.total_epochs}", "execution": head["execution"]},
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "final_loss": head["final_loss"]}
+    if "roofline" in head:
+        line["roofline"] = head["roofline"]
+    for k in ("gemm_in_step", "own_kernel_ms_per_step", "own_calls", "sustained"):
+        if head.get(k) is not None:
+            line[k] = head[k]
+
+    extra = {}
+    if args.workload == "flickr8k" and not args.no_vitb16:
+        # BASELINE config 4 on the same build, same process, same ranks (eager; fewer steps: ~0.3 s each)
+        vsteps = min(args.steps, args.vit_steps)
+        v = measure_workload(args, T.VITB16, vsteps, 3, ctx, False, None)
+        extra["vitb16"] = {"workload": T.VITB16.name, "value": v["value"], "unit": UNIT, "ms_per_step": v["ms_per_step"],
+                           "steps": vsteps, "e2e": v["e2e"]["value"], "gpu_launches": v["gpu_launches"],
+                           "roofline": v.get("roofline"), "gemm_in_step": v.get("gemm_in_step"), "own_calls": v["own_calls"],
+                           "final_loss": v["final_loss"], "mode": args.mode}
     if rank == 0:
-        summ = prof.summary()
-        own_ms = sum(d["ms"] for d in summ.values()) / 2
-        top = max(summ.items(), key=lambda kv: kv[1]["ms"]) if summ else None
-        tf_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        src = "of measured" if peaks["_source"] == "measured" else "of fallback"
-        if top is not None:
-            name, d = top
-            if d["flops"] > 0:
-                ach = d["flops"] / (d["ms"] * 1e-3) / 1e12
-                line["roofline"] = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": tf_peak,
-                                    "unit": "TFLOP/s", "frac": round(ach / tf_peak, 5), "traffic": None,
-                                    "peak_kind": f"bf16 sustained {src}", "calls_per_step": d["calls"] // 2,
-                                    "ms_per_step": round(d["ms"] / 2, 4),
-                                    "share_of_own_kernel_time": round(d["ms"] / 2 / max(own_ms, 1e-9), 3),
-                                    "note": "useful flops 2*rows*cols*k per call; shapes of this config are "
-                                            "launch/latency bound (SURVEY H10) -- see rooflines[] for config 3/5 shapes"}
-            else:
-                line["roofline"] = {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"],
-                                    "unit": "GB/s", "frac": None, "traffic": None, "ms_per_step": round(d["ms"] / 2, 4)}
-        line["own_kernel_ms_per_step"] = round(own_ms, 4)
-        line["own_calls"] = {k: {"calls_per_step": v["calls"] // 2, "ms_per_step": round(v["ms"] / 2, 4)} for k, v in
-                             sorted(summ.items(), key=lambda kv: -kv[1]["ms"])[:8]}
         if world == 1 and not args.no_kernel_rooflines:
-            line["rooflines"] = kernel_rooflines(device, peaks, flush)
+            flush = ctx["flush"]
+            rl = attention_rooflines(device, peaks, flush) + streaming_rooflines(device, peaks, flush) + gemm_rooflines(device, peaks, flush)
+            line["rooflines"] = rl
         if world == 1 and not args.no_cpu_baseline:
-            v, s_per = cpu_port_throughput(cfg, args.cpu_steps, 1)
-            line["cpu_baseline"] = {"value": round(v, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{args.cpu_steps} full optimisation steps of the same config (batch "
-                                              f"{cfg.batch}) on the CPU port of the reference algorithm (oracle/), "
-                                              f"{round(s_per, 3)} s/step"}
+            line["cpu_baseline"] = cpu_baseline_subprocess(args, args.workload)
+        if world == 1 and not args.no_dropin and cfg.image_tower == "resnet18":
+            try:
+                line["dropin"] = measure_dropin(args, cfg, args.steps, args.warmup, ctx)
+            except Exception as exc:
+                line["dropin"] = {"unavailable": repr(exc)[:300]}
+        if extra:
+            line["configs"] = extra
+        # ---- compact summary, last in the line
+        summary = {"config2_samples_per_s": line["value"], "config2_e2e": line["e2e"]["value"]}
+        if "vitb16" in extra:
+            summary["config4_samples_per_s"] = extra["vitb16"]["value"]
+            summary["config4_ms_per_step"] = extra["vitb16"]["ms_per_step"]
+            if extra["vitb16"].get("gemm_in_step"):
+                summary["config4_gemm_frac_in_step"] = extra["vitb16"]["gemm_in_step"]["frac_of_sustained_peak"]
+        if "dropin" in line and "value" in line["dropin"]:
+            summary["dropin_samples_per_s"] = line["dropin"]["value"]
+        if line.get("cpu_baseline", {}).get("value"):
+            summary["reference_cpu_samples_per_s"] = line["cpu_baseline"]["value"]
+            summary["reference_kind"] = line["cpu_baseline"]["kind"]
+        for r in line.get("rooflines", []):
+            if r.get("bound") == "tensor" and "fwdbwd_ms" in r:
+                summary["c3 " + r["workload"].split("config3 ")[1].replace(", 8192 tokens", "") + " fwd/fwdbwd frac"] = [r["fwd_frac"], r["frac"]]
+            elif r.get("bound") == "hbm":
+                summary["c5 " + r["kernel"] + (" 1B" if "layers" in r["workload"] else " 4096^2")] = r["frac"]
+        line["summary"] = summary
         print(json.dumps(line), flush=True)
     if world > 1:
-        # tear down in a fixed order (captured NCCL kernels first); a watchdog guarantees the process
-        # exits even if communicator destruction stalls
+        # tear down in a fixed order; a watchdog guarantees the process exits even if communicator destruction stalls
         sys.stdout.flush()
         threading.Timer(30.0, lambda: os._exit(0)).start()
         torch.cuda.synchronize()
         torch.distributed.barrier()
-        if gstep is not None:
-            gstep.graph.reset()
-            del gstep
         torch.cuda.synchronize()
         try:
             torch.distributed.destroy_process_group()
@@ -504,16 +714,19 @@ def main():
     ap.add_argument("--mode", choices=["parity", "fast"], default="parity")
     ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch (debug only; invalidates the number)")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--vit-steps", type=int, default=8, help="timed steps of the config-4 sub-run")
+    ap.add_argument("--sustained-steps", type=int, default=400, help="extra back-to-back graph replays (timed region >= 1 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of as one CUDA graph")
     ap.add_argument("--no-kernel-rooflines", action="store_true")
+    ap.add_argument("--no-vitb16", action="store_true", help="skip the config-4 sub-run")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the reference-models-on-this-atq arm")
     ap.add_argument("--serial-towers", action="store_true", help="run the image and text towers on one stream (no graph branch concurrency)")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of atq.optim.FlatAdamW")
     ap.add_argument("--sparse-grads", action="store_true", help="N>1: all-reduce only the masked entries of RPB weight gradients")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     from workloads import train as T
-    import dataclasses
     cfg = T.FLICKR8K_SHAPE if args.workload == "flickr8k" else T.VITB16
     if args.batch:
         cfg = dataclasses.replace(cfg, batch=args.batch, name=cfg.name + f" [DEBUG batch {args.batch}]")

@@ -106,20 +106,32 @@ int atq_route_mask_mul(int device, const float* x, const float* grad_out, const 
                        float* grad_in, atq_stream_t stream);
 
 /* ---- GEMM operand builders ----------------------------------------------------------- */
-/* fp32 [rows, cols] (row pitch ld_in elements) -> bf16 hi (+ lo = bf16(x - hi), nullable)
- * [rows, pitch]; pitch % 8 == 0, pitch >= cols; padding columns are left untouched. */
+/* Operand element formats (both are 16-bit pairs consumed by tcgen05.mma kind::f16, same MMA count):
+ *   scale_slot == NULL : bf16 pair, hi = bf16(x), lo = bf16(x - hi)                      (~16 significant bits)
+ *   scale_slot != NULL : scaled fp16 pair, hi = fp16(s x), lo = fp16(s x - hi), s = scale_slot[1] a power of two
+ *                        chosen per tensor so that max|s x| is in [2^14, 2^15)            (~22 significant bits);
+ *                        the GEMM multiplies its accumulator by scale_slot[2] = 1/s (atq_bf16_operand.inv_scale).
+ * A scale slot is 4 caller-owned floats {scratch, s, 1/s, scratch}; slot[0] and slot[3] must be zero before the
+ * first atq_absmax_scale on it and are zero again when that call's kernel has finished (graph replays re-arm it).
+ * bound = max(max|x|, |*extra|) * bound_mul lets a producer reserve head-room for a derived tensor
+ * (e.g. |dropout(gelu(y))| <= max|y| / (1-p)); extra is a nullable device scalar. */
+int atq_absmax_scale(int device, const float* x, int64_t rows, int64_t cols, int64_t ld, float bound_mul,
+                     const float* extra, float* slot, atq_stream_t stream);
+/* fp32 [rows, cols] (row pitch ld_in elements) -> hi (+ lo, nullable) [rows, pitch]; pitch % 8 == 0,
+ * pitch >= cols; padding columns are left untouched. */
 int atq_split_bf16(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in,
-                   uint16_t* hi, uint16_t* lo, int64_t pitch, atq_stream_t stream);
+                   uint16_t* hi, uint16_t* lo, int64_t pitch, const float* scale_slot, atq_stream_t stream);
 /* split of a contiguous [rows, cols] tensor (cols % 8 == 0) fused with its column sums
  * (colsum_out[c] = sum_r x[r,c], deterministic two-stage): one pass over dY yields the GEMM
  * operand and the bias gradient. */
 size_t atq_workspace_bytes_split_colsum(int64_t rows, int64_t cols);
 int atq_split_bf16_colsum(int device, const float* x, int64_t rows, int64_t cols, uint16_t* hi, uint16_t* lo,
-                          float* colsum_out, void* ws, size_t ws_bytes, atq_stream_t stream);
+                          float* colsum_out, void* ws, size_t ws_bytes, const float* scale_slot, atq_stream_t stream);
 /* same, transposed output: hi_t/lo_t are [cols, pitch_t], pitch_t % 8 == 0, pitch_t >= rows.
  * colsum is reserved (must be NULL; use atq_colsum_f32). */
 int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in,
-                     uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, float* colsum, atq_stream_t stream);
+                     uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, float* colsum, const float* scale_slot,
+                     atq_stream_t stream);
 
 /* Quantize a layer into everything its GEMMs consume, in one pass over W [M,K]:
  *  packed   : 2-bit codec bytes of T (public format, flat row-major), nullable; K % 4 == 0
@@ -129,14 +141,16 @@ int atq_split_bf16_t(int device, const float* x, int64_t rows, int64_t cols, int
  * replaces atq/quantizers.py:41-43 + the `w_ternary * alpha` materialisation of atq/layers.py:43. */
 int atq_build_ternary_operands(int device, const float* w, int64_t M, int64_t K, const float* thr,
                                uint8_t* packed, uint8_t* packed_t, uint16_t* tb, int64_t pitch,
-                               uint16_t* tb_t, int64_t pitch_t, void* stats, atq_stream_t stream);
+                               uint16_t* tb_t, int64_t pitch_t, void* stats, int fp16 /* tb, tb_t as fp16 */,
+                               atq_stream_t stream);
 /* Residual-precision-boost mixed weight (atq/precision_boost.py:72):
  *  Wm = T*alpha*(1-mask) + W*mask, emitted as bf16 hi/lo pairs [M,pitch] and transposed
  *  [K,pitch_t]; lo pointers nullable (fast mode).  packed as above (nullable). */
 int atq_build_mixed_operands(int device, const float* w, const float* mask, int64_t M, int64_t K,
                              const float* thr, const float* alpha, uint8_t* packed,
                              uint16_t* hi, uint16_t* lo, int64_t pitch,
-                             uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, atq_stream_t stream);
+                             uint16_t* hi_t, uint16_t* lo_t, int64_t pitch_t, const float* scale_slot,
+                             atq_stream_t stream);
 
 /* ---- ternary GEMMs (tcgen05 / TMEM / TMA) -------------------------------------------- */
 /* Common operand description: a bf16 matrix given as hi (+ optional lo) so that the fp32 value
@@ -151,7 +165,8 @@ typedef struct {
   const uint16_t* lo; /* nullable */
   int64_t pitch;
   int32_t mn_major;
-  int32_t reserved;
+  int32_t format;          /* 0 = bf16, 1 = fp16; A and B of one GEMM must agree */
+  const float* inv_scale;  /* nullable device scalar: the accumulator is multiplied by it (1/s of a scaled operand) */
 } atq_bf16_operand;
 
 /* K7 forward:  Y[N,M] = scale * (X[N,K] . B[M,K]^T) + bias      (atq/layers.py:43,
@@ -232,10 +247,11 @@ int atq_attention_bwd(int device, int B, int H, int L, const float* q, int64_t q
  *           its column sums (bias gradient); ws >= atq_workspace_bytes_split_colsum(rows, cols).
  * The dropout mask is regenerated from the counter hash of (seed, flat index): pass the same seed / p. */
 int atq_gelu_dropout_split(int device, const float* y, int64_t rows, int64_t cols, float dropout_p,
-                           const unsigned long long* seed, uint16_t* hi, uint16_t* lo, atq_stream_t stream);
+                           const unsigned long long* seed, uint16_t* hi, uint16_t* lo, const float* scale_slot,
+                           atq_stream_t stream);
 int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y, int64_t rows, int64_t cols, float dropout_p,
                                       const unsigned long long* seed, uint16_t* hi, uint16_t* lo, float* colsum_out,
-                                      void* ws, size_t ws_bytes, atq_stream_t stream);
+                                      void* ws, size_t ws_bytes, const float* scale_slot, atq_stream_t stream);
 
 /* Gated residual of the ternary transformer block (models/text_encoder.py:238-249):
  *   out = src + dropout(h) * g   with g = sigmoid(gate) a device scalar; n % 4 == 0, contiguous tensors.
