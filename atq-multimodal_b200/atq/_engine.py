@@ -205,6 +205,19 @@ def absmax_slot(x2: torch.Tensor, bound_mul: float = 1.0, extra: Optional[torch.
     return slot
 
 
+def absmax_slots_batched(tensors, extras=None, bound_mul: float = 1.0):
+    """Scale slots of many contiguous tensors in one launch (extras: per-tensor device scalars joining the maximum)."""
+    count = len(tensors)
+    dev = nv.device_index(tensors[0])
+    slots = [nv.new_slot(tensors[0].device) for _ in range(count)]
+    x_arr = (ctypes.c_void_p * count)(*[t.data_ptr() for t in tensors])
+    n_arr = (ctypes.c_int64 * count)(*[t.numel() for t in tensors])
+    e_arr = (ctypes.c_void_p * count)(*[None if e is None else e.data_ptr() for e in (extras or [None] * count)])
+    s_arr = (ctypes.c_void_p * count)(*[sl.data_ptr() for sl in slots])
+    nv.call("atq_absmax_scale_batched", dev, count, x_arr, n_arr, e_arr, s_arr, float(bound_mul), nv.stream_ptr(dev))
+    return slots
+
+
 def split_bf16(x2: torch.Tensor, want_lo: bool, slot: Optional[torch.Tensor] = None):
     """fp32 [rows, cols] -> (hi, lo|None, pitch) row-major: bf16 pair, or (when a scale slot is given) the scaled
     fp16 pair as (hi, lo, pitch, 0, slot)."""
@@ -219,10 +232,49 @@ def split_bf16(x2: torch.Tensor, want_lo: bool, slot: Optional[torch.Tensor] = N
     return (hi, lo, pitch) if slot is None else (hi, lo, pitch, 0, slot)
 
 
-def split_operand(x2: torch.Tensor):
+_FUSED_MAX = int(nv.lib.atq_split_scaled_fused_max_elems())
+
+
+def split_scaled(x2: torch.Tensor, want_lo: bool = True):
+    """Scaled-fp16 operand of a contiguous fp32 [rows, cols] tensor: one cluster kernel (max|x|, scale, split) for
+    small tensors, the grid-level reduction followed by the streaming split otherwise."""
+    rows, cols = x2.shape
+    n = rows * cols
+    if _FUSED_SPLIT and n <= _FUSED_MAX and cols % 8 == 0 and x2.stride(0) == cols and x2.data_ptr() % 16 == 0:
+        dev = nv.device_index(x2)
+        hi = torch.empty((rows, cols), dtype=torch.float16, device=x2.device)
+        lo = torch.empty((rows, cols), dtype=torch.float16, device=x2.device) if want_lo else None
+        slot = nv.new_slot(x2.device)
+        nv.call("atq_split_scaled_fused", dev, x2.data_ptr(), n, hi.data_ptr(), nv.ptr(lo), 1.0, None, slot.data_ptr(),
+                nv.stream_ptr(dev))
+        return (hi, lo, cols, 0, slot)
+    return split_bf16(x2, want_lo, absmax_slot(x2))
+
+
+# q_proj / k_proj / v_proj of a self-attention block receive the SAME tensor (models/text_encoder.py:82-84): the
+# last operand built on each stream is kept (with a strong reference to its source, so the memory cannot be recycled
+# under it) and reused while the source's (storage, version, layout, mode) still match.
+_LAST_SPLIT: dict = {}
+# (opt-in: under CUDA-graph capture of the whole step the reuse invalidates the capture -- cause not found -- and it
+#  saves two small launches per attention block, so it stays off by default)
+_SPLIT_REUSE = os.environ.get("ATQ_SPLIT_REUSE", "0") == "1"
+_FUSED_SPLIT = os.environ.get("ATQ_FUSED_SPLIT", "1") == "1"
+
+
+def split_operand(x2: torch.Tensor, owner: Optional[torch.Tensor] = None):
     """The A operand of a GEMM in the current precision mode (see the module docstring)."""
+    if owner is not None and _SPLIT_REUSE:
+        capturing = torch.cuda.is_current_stream_capturing()
+        skey = (nv.device_index(x2), nv.stream_ptr(nv.device_index(x2)), capturing)
+        key = (x2.data_ptr(), owner._version, tuple(x2.shape), tuple(x2.stride()), _MODE)
+        hit = _LAST_SPLIT.get(skey)
+        if hit is not None and hit[0] == key and hit[1] is owner:
+            return hit[2]
+        op = split_operand(x2)
+        _LAST_SPLIT[skey] = (key, owner, op, x2)
+        return op
     if _use_f16():
-        return split_bf16(x2, True, absmax_slot(x2))
+        return split_scaled(x2)
     hi, lo, pitch = split_bf16(x2, _use_lo())
     return (hi, lo, pitch, 0, None)
 
@@ -252,6 +304,8 @@ def split_bf16_colsum(x2: torch.Tensor, want_lo: bool, slot: Optional[torch.Tens
 
 def split_operand_colsum(x2: torch.Tensor, want_lo: bool, f16: bool):
     """Operand split + column sums with the format of the OTHER operand of the GEMMs it feeds (saved from forward)."""
+    if f16 and _FUSED_SPLIT and x2.numel() <= _FUSED_MAX and x2.shape[1] % 8 == 0 and x2.stride(0) == x2.shape[1] and x2.data_ptr() % 16 == 0:
+        return split_scaled(x2, want_lo), colsum(x2)  # two launches instead of three
     return split_bf16_colsum(x2, want_lo, absmax_slot(x2) if f16 else None)
 
 
@@ -373,7 +427,7 @@ def _key(weight, alpha, mask, sparsity_target, threshold_factor):
 
 @torch.no_grad()
 def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, threshold_factor=0.05,
-                   thr: Optional[torch.Tensor] = None) -> LayerOperands:
+                   thr: Optional[torch.Tensor] = None, slot: Optional[torch.Tensor] = None) -> LayerOperands:
     """mask None -> TernaryLinear operands (T exact in bf16; alpha applied in the GEMM epilogue).
     mask given -> RPB mixed weight Wm = T*alpha*(1-mask) + W*mask as bf16 hi/lo."""
     key = _key(weight, alpha if mask is not None else None, mask, sparsity_target, threshold_factor)
@@ -392,8 +446,8 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
     packed_t = None
     f16 = _use_f16()
     bf = torch.float16 if f16 else torch.bfloat16
-    slot = None
     if mask is None:
+        slot = None
         # TernaryLinear: the GEMMs read the 2-bit codec bytes directly whenever the contraction
         # dimension allows 16-byte codec rows per k-block; 16-bit copies only for odd shapes.  T is exact in
         # bf16 and in fp16 (no scale): the copy just has to carry the element format of the activations.
@@ -412,7 +466,9 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
         hi_t = lo_t = None  # dX reads hi/lo in place through MN-major descriptors
         mk = nv.require_f32(mask, "precision_mask")
         al = nv.require_f32(alpha.detach(), "alpha")
-        if f16:  # |Wm| <= max(max|W|, |alpha|): one reduction over W gives the scale of the mixed operand
+        if not f16:
+            slot = None
+        elif slot is None:  # |Wm| <= max(max|W|, |alpha|): one reduction over W gives the scale of the mixed operand
             slot = absmax_slot(w, 1.0, al)
         nv.call("atq_build_mixed_operands", dev, w.data_ptr(), mk.data_ptr(), M, K, thr.data_ptr(), al.data_ptr(),
                 packed.data_ptr() if flat_ok else None, hi.data_ptr(), nv.ptr(lo), pitch, None, None, pitch_t,
@@ -444,8 +500,14 @@ def prepare_quantization(model, threshold_factor=0.05) -> int:
     if not stale:
         return 0
     thr = adaptive_threshold_batched([m.weight.detach() for m, *_ in stale], [s for *_, s in stale], threshold_factor)
+    slots = [None] * len(stale)
+    rpb = [i for i, (m, cache, alpha, mask, s) in enumerate(stale) if mask is not None and m.weight.is_contiguous()]
+    if _use_f16() and rpb:  # per-layer scales of the mixed weights: one launch for all layers
+        got = absmax_slots_batched([stale[i][0].weight.detach() for i in rpb], [stale[i][0].alpha.detach() for i in rpb])
+        for i, sl in zip(rpb, got):
+            slots[i] = sl
     for i, (m, cache, alpha, mask, s) in enumerate(stale):
-        layer_operands(cache, m.weight, m.alpha, mask, s, threshold_factor, thr=thr[i])
+        layer_operands(cache, m.weight, m.alpha, mask, s, threshold_factor, thr=thr[i], slot=slots[i])
     return len(stale)
 
 
@@ -457,6 +519,7 @@ class _TernaryLinearFn(torch.autograd.Function):
     """y = x (alpha T)^T + b   (atq/layers.py:35-43)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, weight, alpha, bias, ops: LayerOperands):
         M, K = weight.shape
         x2 = nv.require_f32(x, "input").reshape(-1, K)
@@ -467,7 +530,7 @@ class _TernaryLinearFn(torch.autograd.Function):
         if N == 0:
             y = x2.new_zeros((0, M))
         else:
-            xa = split_operand(x2)
+            xa = split_operand(x2, x)
             b_ = None if bias is None else bias.detach()
             if _want_packed(N) and packed_gemm_ok(K, ops.packed):
                 # packed 2-bit weights, expanded to bf16 tiles inside the GEMM
@@ -484,6 +547,7 @@ class _TernaryLinearFn(torch.autograd.Function):
         return y.reshape(*x.shape[:-1], M)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gy):
         x2, al = ctx.saved_tensors
         M, K = ctx.wshape
@@ -497,7 +561,7 @@ class _TernaryLinearFn(torch.autograd.Function):
         if ctx.has_bias:
             ga, dbias = split_operand_colsum(g2, want_lo, f16)  # one pass over dY: operand split + bias gradient
         else:
-            ga, dbias = split_bf16(g2, want_lo, absmax_slot(g2) if f16 else None), None
+            ga, dbias = (split_scaled(g2, want_lo) if f16 else split_bf16(g2, want_lo)), None
         # dX = alpha * (dY . T);  d(alpha) = sum((dY . T) .* X) fused in the same epilogue
         if _want_packed(N) and packed_gemm_ok(M, ctx.packed_t):
             dx, dalpha = tgemm_packed(ga, ctx.packed_t, N, K, M, scale=al, dot_ref=x2)
@@ -505,7 +569,7 @@ class _TernaryLinearFn(torch.autograd.Function):
             dx, dalpha = tgemm(ga, ctx.ops_w_t, N, K, M, scale=al, dot_ref=x2)
         dw = None
         if ctx.ste:  # opt-in straight-through estimator: dW = G (dY and X consumed MN-major, no transposes)
-            xa = split_bf16(x2, want_lo, absmax_slot(x2) if f16 else None)
+            xa = split_scaled(x2, want_lo) if f16 else split_bf16(x2, want_lo)
             dw, _ = tgemm_dw_masked(mn_view(ga), mn_view(xa), M, K, N)
         return dx.reshape(ctx.xshape), dw, dalpha, dbias, None
 
@@ -514,6 +578,7 @@ class _RPBLinearFn(torch.autograd.Function):
     """y = x Wm^T + b,  Wm = T*alpha*(1-mask) + W*mask   (atq/precision_boost.py:62-74)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, weight, alpha, bias, mask, ops: LayerOperands):
         M, K = weight.shape
         x2 = nv.require_f32(x, "input").reshape(-1, K)
@@ -523,7 +588,7 @@ class _RPBLinearFn(torch.autograd.Function):
         if N == 0:
             y = x2.new_zeros((0, M))
         else:
-            xa = split_operand(x2)
+            xa = split_operand(x2, x)
             y, _ = tgemm(xa, ops.w, N, M, K, scale=None, bias=None if bias is None else bias.detach())
         # backward consumes the SAME (hi, lo) split of x (MN-major, as the dW B operand): save it
         # instead of the fp32 activations (same bytes), so nothing is split or transposed twice
@@ -543,6 +608,7 @@ class _RPBLinearFn(torch.autograd.Function):
         return y.reshape(*x.shape[:-1], M)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gy):
         saved = ctx.saved_tensors
         mask = saved[-1]
@@ -559,7 +625,7 @@ class _RPBLinearFn(torch.autograd.Function):
         if ctx.has_bias:  # ONE pass over dY: the split feeds both backward GEMMs, the column sums are d(bias)
             ga, dbias = split_operand_colsum(g2, xa[1] is not None, f16)
         else:
-            ga, dbias = split_bf16(g2, xa[1] is not None, absmax_slot(g2) if f16 else None), None
+            ga, dbias = (split_scaled(g2, xa[1] is not None) if f16 else split_bf16(g2, xa[1] is not None)), None
             if len(ga) == 3:
                 ga = ga + (0, None)
         dx = None
@@ -610,6 +676,7 @@ class _RPBFFNFn(torch.autograd.Function):
     streaming kernel per direction, the [tokens, hidden] gelu / dropout outputs never exist in fp32."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, w1, alpha1, b1, mask1, ops1, w2, alpha2, b2, mask2, ops2, p, seed):
         H, K = w1.shape
         M = w2.shape[0]
@@ -618,7 +685,7 @@ class _RPBFFNFn(torch.autograd.Function):
             x2 = x2.contiguous()
         N = x2.shape[0]
         lo, f16 = _use_lo(), _use_f16()
-        xa = split_operand(x2)
+        xa = split_operand(x2, x)
         y1, _ = tgemm(xa, ops1.w, N, H, K, bias=None if b1 is None else b1.detach())
         # |dropout(gelu(y))| <= max|y| / (1-p): the hidden operand's scale comes from one reduction over y1
         da = gelu_dropout_split(y1, p, seed, lo, absmax_slot(y1, _keep_bound(p)) if f16 else None)
@@ -633,6 +700,7 @@ class _RPBFFNFn(torch.autograd.Function):
         return y2.reshape(*x.shape[:-1], M)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gy):
         N, K, H, M, p, lo, x_pitch, has_b1, has_b2 = ctx.cfg
         saved = ctx.saved_tensors
@@ -647,7 +715,7 @@ class _RPBFFNFn(torch.autograd.Function):
         if has_b2:
             ga2, db2 = split_operand_colsum(g2, lo, f16)
         else:
-            ga2, db2 = split_bf16(g2, lo, absmax_slot(g2) if f16 else None), None
+            ga2, db2 = (split_scaled(g2, lo) if f16 else split_bf16(g2, lo)), None
         dd, _ = tgemm(ga2, w2_t, N, H, M)  # gradient w.r.t. the dropped activations, fp32 [N, H]
         mk2 = mask2 if mask2.is_contiguous() else mask2.contiguous()
         dw2, dalpha2 = tgemm_dw_masked(mn_view(ga2), mn_view(da), M, H, N, mask=mk2, packed=packed2)
@@ -686,6 +754,7 @@ class _GatedResidualFn(torch.autograd.Function):
     """out = src + dropout(h) * g  (g: 1-element tensor, e.g. sigmoid(gate); models/text_encoder.py:238-249)."""
 
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, src, h, g, p, seed):
         src_c = nv.require_f32(src, "src")
         h_c = nv.require_f32(h, "h")
@@ -699,6 +768,7 @@ class _GatedResidualFn(torch.autograd.Function):
         return out.view(src.shape)
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
         h_c, g_c = ctx.saved_tensors
         d = nv.require_f32(dout, "grad_output")

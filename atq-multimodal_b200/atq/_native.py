@@ -54,6 +54,10 @@ _SIGS = {
     "atq_unpack2_to_i8": (c_int, [c_int, _P, c_int64, _P, _P]),
     "atq_route_mask_mul": (c_int, [c_int, _P, _P, _P, c_int64, _P, _P]),
     "atq_absmax_scale": (c_int, [c_int, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
+    "atq_absmax_scale_batched": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), POINTER(c_void_p),
+                                         c_float, _P]),
+    "atq_split_scaled_fused_max_elems": (c_int64, []),
+    "atq_split_scaled_fused": (c_int, [c_int, _P, c_int64, _P, _P, c_float, _P, _P, _P]),
     "atq_split_bf16": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, _P]),
     "atq_workspace_bytes_split_colsum": (c_size_t, [c_int64, c_int64]),
     "atq_split_bf16_colsum": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P, _P]),

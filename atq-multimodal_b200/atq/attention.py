@@ -46,6 +46,7 @@ def _terms() -> int:
 
 class _AttentionCoreFn(torch.autograd.Function):
     @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, q, k, v, num_heads, key_padding, scale, dropout_p, seed):
         q, qp = _rows(q, "q")
         k, kp = _rows(k, "k")
@@ -67,6 +68,7 @@ class _AttentionCoreFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dout):
         q, k, v, out, lse, key_padding, seed = ctx.saved_tensors
         num_heads, scale, dropout_p, terms, qp, kp, vp = ctx.cfg

@@ -4,7 +4,9 @@ Same update as `torch.optim.AdamW` (decoupled weight decay, bias correction, no 
 train_multimodal.py:361-366 optimizer).  torch's fused multi-tensor implementation reaches ~13 % of the copy
 roofline on the ~120 mostly small tensors of the Flickr8k-shape model; this one walks a host-built table of
 1024-element chunks and runs at the streaming rate.  Parameters whose `.grad` is None are skipped exactly like
-torch does (TernaryLinear.weight, modules off the training path - SURVEY 8a G).  CUDA-graph capturable: the step
+torch does (TernaryLinear.weight, modules off the training path - SURVEY 8a G).  One step counter per parameter
+group (torch keeps one per parameter: they differ only for a parameter whose first gradient arrives later than
+its group's, which does not occur on this path).  CUDA-graph capturable: the step
 counter lives on the device and the pointer table is uploaded from pinned host memory.
 """
 from __future__ import annotations
@@ -25,27 +27,44 @@ class FlatAdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
 
+    def load_state_dict(self, state_dict):
+        """Resume: the moment buffers are replaced by the loaded ones, so every cached pointer table is stale; the
+        per-group step counter comes back wherever torch.load put it and must live on the parameters' device."""
+        super().load_state_dict(state_dict)
+        self._tables = {}
+        for group in self.param_groups:
+            step = group.get("step")
+            dev = next((p.device for p in group["params"]), None)
+            if step is not None and dev is not None:
+                group["step"] = torch.as_tensor(step, dtype=torch.float32).reshape(1).to(dev)
+
     def _table(self, gi, group):
         ps = [p for p in group["params"] if p.grad is not None]
         if not ps:
             return None
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
-        cached = self._tables.get(gi)
-        if cached is not None and cached["key"] == key:
-            return cached
         dev = ps[0].device
-        rows, chunk_tensor, chunk_off, grads = [], [], [], []
-        for i, p in enumerate(ps):
+        if "step" not in group:
+            group["step"] = torch.zeros(1, dtype=torch.float32, device=dev)
+        for p in ps:
             if p.dtype != torch.float32 or not p.is_cuda:
                 raise RuntimeError("FlatAdamW: parameters must be float32 CUDA tensors")
             st = self.state[p]
             if not st:
                 st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        # every pointer the kernel dereferences is part of the key (a reloaded state or a re-allocated gradient
+        # rebuilds the table); the cache holds no tensor references
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(), self.state[p]["exp_avg_sq"].data_ptr())
+                    for p in ps) + (group["step"].data_ptr(),)
+        cached = self._tables.get(gi)
+        if cached is not None and cached["key"] == key:
+            return cached
+        rows, chunk_tensor, chunk_off = [], [], []
+        for i, p in enumerate(ps):
+            st = self.state[p]
             g = p.grad
             if g.stride() != p.stride() or g.dtype != torch.float32:
                 raise RuntimeError("FlatAdamW: a gradient does not share its parameter's memory layout")
-            grads.append(g)
             rows.append(struct.pack("<QQQQq", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()))
             nch = (p.numel() + _CHUNK - 1) // _CHUNK
             chunk_tensor += [i] * nch
@@ -56,9 +75,7 @@ class FlatAdamW(torch.optim.Optimizer):
         meta_d = torch.empty_like(meta, device=dev)
         table.copy_(host, non_blocking=True)       # pinned -> device: legal inside a CUDA-graph capture
         meta_d.copy_(meta, non_blocking=True)
-        if "step" not in group:
-            group["step"] = torch.zeros(1, dtype=torch.float32, device=dev)
-        cached = dict(key=key, table=table, meta=meta_d, host=(host, meta), n_chunks=len(chunk_tensor), grads=grads)
+        cached = dict(key=key, table=table, meta=meta_d, host=(host, meta), n_chunks=len(chunk_tensor))
         self._tables[gi] = cached
         return cached
 

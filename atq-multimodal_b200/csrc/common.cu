@@ -6,7 +6,6 @@
 namespace atq {
 
 static thread_local char g_err[512] = "";
-static thread_local int g_cur_device = -1;
 static int g_sm_count[64] = {0};
 
 static std::atomic<unsigned long long> g_launches{0};
@@ -22,20 +21,27 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int ensure_device(int device) {
+int DeviceGuard::set(int device) {
+  // The caller (PyTorch) owns the thread's current device and changes it behind this library's back (device guards,
+  // torch.cuda.set_device, the autograd thread), so nothing is cached: ask, switch only when it differs, and put the
+  // caller's device back when the entry point returns.
   if (device < 0 || device >= 64) {
     set_error("bad device index %d", device);
     return ATQ_EINVAL;
   }
-  if (g_cur_device != device) {
-    cudaError_t e = cudaSetDevice(device);
-    if (e != cudaSuccess) {
-      set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
-      return ATQ_ECUDA;
-    }
-    g_cur_device = device;
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e == cudaSuccess && cur == device) return ATQ_OK;
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    set_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+    return ATQ_ECUDA;
   }
+  prev = cur;
   return ATQ_OK;
+}
+DeviceGuard::~DeviceGuard() {
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 int sm_count(int device) {

@@ -16,9 +16,13 @@ constexpr int kNumSMsB200 = 148;
 char* last_error_buf();
 void set_error(const char* fmt, ...);
 
-// Make `device` current on the calling thread (autograd's backward thread starts on device 0
-// from this library's statically linked runtime's point of view).
-int ensure_device(int device);
+// Makes `device` current on the calling thread for the duration of one entry point (autograd's backward thread
+// starts on device 0 from this library's statically linked runtime's point of view) and restores the caller's.
+struct DeviceGuard {
+  int prev = -1;
+  int set(int device);
+  ~DeviceGuard();
+};
 int sm_count(int device);
 void note_launch(int n = 1);  // kernel-launch counter reported by atq_kernel_launch_count()
 
@@ -49,10 +53,11 @@ void note_launch(int n = 1);  // kernel-launch counter reported by atq_kernel_la
     atq::note_launch();                                                                  \
   } while (0)
 
-#define ATQ_ENSURE_DEVICE(dev)              \
-  do {                                      \
-    int r__ = atq::ensure_device(dev);      \
-    if (r__ != ATQ_OK) return r__;          \
+#define ATQ_ENSURE_DEVICE(dev)                  \
+  atq::DeviceGuard device_guard__;              \
+  do {                                          \
+    int r__ = device_guard__.set(dev);          \
+    if (r__ != ATQ_OK) return r__;              \
   } while (0)
 
 // grid for a grid-stride streaming kernel: enough CTAs to cover `work_items` once at

@@ -2,6 +2,7 @@
 // routing mask-multiply, bf16 operand builders.  All are coalesced 128-bit load/store,
 // grid-stride kernels sized in multiples of the SM count; integer outputs are bit-exact
 // against the reference (atq/quantizers.py:41-43, atq/bit_packing.py:45-69,104-119).
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace atq {
@@ -333,6 +334,123 @@ __global__ void __launch_bounds__(kThreads)
       slot[2] = inv;
       bits[3] = 0u;
     }
+  }
+}
+
+// many tensors, one launch (the per-layer weight scales of a model: blockIdx.y = tensor); contiguous tensors only
+constexpr int kAbsmaxBatch = 64;
+struct AbsmaxBatch {
+  const float* x[kAbsmaxBatch];
+  long long n[kAbsmaxBatch];
+  const float* extra[kAbsmaxBatch];
+  float* slot[kAbsmaxBatch];
+};
+__global__ void __launch_bounds__(kThreads) absmax_scale_batched_kernel(const AbsmaxBatch b, float bound_mul) {
+  const float* __restrict__ x = b.x[blockIdx.y];
+  const long long n = b.n[blockIdx.y];
+  float* slot = b.slot[blockIdx.y];
+  const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long g = t; g < n4; g += stride) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + g);
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (t == 0)
+      for (long long i = n4 * 4; i < n; ++i) m = fmaxf(m, fabsf(x[i]));
+  } else {
+    for (long long i = t; i < n; i += stride) m = fmaxf(m, fabsf(__ldg(x + i)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float s_m[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) m = fmaxf(m, s_m[i]);
+    unsigned int* bits = reinterpret_cast<unsigned int*>(slot);
+    atomicMax(bits, __float_as_uint(m));
+    __threadfence();
+    if (atomicAdd(bits + 3, 1u) == gridDim.x - 1) {
+      __threadfence();
+      float bound = __uint_as_float(atomicExch(bits, 0u));
+      const float* extra = b.extra[blockIdx.y];
+      if (extra != nullptr) bound = fmaxf(bound, fabsf(__ldg(extra)));
+      bound *= bound_mul;
+      float sc, inv;
+      pow2_scale_for(bound, sc, inv);
+      slot[1] = sc;
+      slot[2] = inv;
+      bits[3] = 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Small tensors (<= kFusedSplitMax elements, the launch-bound shapes of BASELINE configs 1-2): max|x| reduction,
+// scale derivation and the scaled-fp16 split in ONE launch.  A thread-block cluster of 8 CTAs (co-scheduled by
+// the hardware, so the cluster barrier cannot dead-lock against other streams) reads the tensor once into
+// registers, exchanges the per-CTA maxima through distributed shared memory, derives the power-of-two scale and
+// writes the operand pair straight from the registers.  slot[1..2] receive {scale, 1/scale} for the GEMM epilogue.
+// ------------------------------------------------------------------------------------
+constexpr int kFusedCtas = 8, kFusedThreads = 512, kFusedVec = 24;  // float4 per thread
+constexpr int64_t kFusedSplitMax = (int64_t)kFusedCtas * kFusedThreads * kFusedVec * 4;  // 393 216 elements
+
+template <bool HAS_LO>
+__global__ void __cluster_dims__(kFusedCtas, 1, 1) __launch_bounds__(kFusedThreads, 1)
+    split_scaled_cluster_kernel(const float* __restrict__ x, int64_t n4, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                float* __restrict__ slot, float bound_mul, const float* __restrict__ extra) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float s_w[kFusedThreads / 32];
+  __shared__ float s_cta_max;
+  const int64_t t = (int64_t)blockIdx.x * kFusedThreads + threadIdx.x;
+  constexpr int64_t kStride = (int64_t)kFusedCtas * kFusedThreads;
+  float4 v[kFusedVec];
+  float m = 0.f;
+#pragma unroll
+  for (int j = 0; j < kFusedVec; ++j) {
+    const int64_t g = t + j * kStride;
+    v[j] = g < n4 ? __ldg(reinterpret_cast<const float4*>(x) + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v[j].x), fabsf(v[j].y))), fmaxf(fabsf(v[j].z), fabsf(v[j].w)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < kFusedThreads / 32; ++i) m = fmaxf(m, s_w[i]);
+    s_cta_max = m;
+  }
+  cluster.sync();  // every CTA's maximum is visible cluster-wide
+  float b = 0.f;
+#pragma unroll
+  for (int r = 0; r < kFusedCtas; ++r) b = fmaxf(b, *cluster.map_shared_rank(&s_cta_max, r));
+  cluster.sync();  // nobody reads remote shared memory after this point
+  if (extra != nullptr) b = fmaxf(b, fabsf(__ldg(extra)));
+  b *= bound_mul;
+  OperandFmt fmt;
+  float inv;
+  fmt.f16 = 1;
+  pow2_scale_for(b, fmt.scale, inv);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    slot[1] = fmt.scale;
+    slot[2] = inv;
+  }
+#pragma unroll
+  for (int j = 0; j < kFusedVec; ++j) {
+    const int64_t g = t + j * kStride;
+    if (g >= n4) continue;
+    uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+    split2(fmt, v[j].x, h0, l0); split2(fmt, v[j].y, h1, l1); split2(fmt, v[j].z, h2, l2); split2(fmt, v[j].w, h3, l3);
+    *reinterpret_cast<uint2*>(hi + 4 * g) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+    if constexpr (HAS_LO)
+      *reinterpret_cast<uint2*>(lo + 4 * g) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
   }
 }
 
@@ -983,6 +1101,49 @@ int atq_absmax_scale(int device, const float* x, int64_t rows, int64_t cols, int
   int grid = vec ? stream_grid(device, (n >> 2) + 1, kThreads * 4, 4)
                  : (int)(rows < (int64_t)sm_count(device) * 4 ? rows : (int64_t)sm_count(device) * 4);
   absmax_scale_kernel<<<grid, kThreads, 0, (cudaStream_t)stream_>>>(x, rows, cols, ld, bound_mul, extra, slot, vec);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+int atq_absmax_scale_batched(int device, int count, const float* const* x_ptrs, const int64_t* ns, const float* const* extra_ptrs,
+                             float* const* slot_ptrs, float bound_mul, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(count > 0 && x_ptrs && ns && slot_ptrs && bound_mul > 0.f, "null pointer, count <= 0 or bound_mul <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  for (int base = 0; base < count; base += kAbsmaxBatch) {
+    const int m = count - base < kAbsmaxBatch ? count - base : kAbsmaxBatch;
+    AbsmaxBatch b;
+    memset(&b, 0, sizeof(b));
+    int64_t nmax = 1;
+    for (int i = 0; i < m; ++i) {
+      ATQ_CHECK_ARG(x_ptrs[base + i] && slot_ptrs[base + i] && ns[base + i] > 0, "null tensor / slot or empty tensor in the batch");
+      b.x[i] = x_ptrs[base + i];
+      b.n[i] = ns[base + i];
+      b.extra[i] = extra_ptrs ? extra_ptrs[base + i] : nullptr;
+      b.slot[i] = slot_ptrs[base + i];
+      if (ns[base + i] > nmax) nmax = ns[base + i];
+    }
+    // enough CTAs per tensor for the largest one, a whole number of waves overall
+    int per = stream_grid(device, (nmax >> 2) + 1, kThreads * 4, 4);
+    const int cap = (sm_count(device) * 4 + m - 1) / m;
+    if (per > cap) per = cap;
+    if (per < 1) per = 1;
+    absmax_scale_batched_kernel<<<dim3((unsigned)per, (unsigned)m), kThreads, 0, (cudaStream_t)stream_>>>(b, bound_mul);
+    ATQ_LAUNCH_CHECK();
+  }
+  return ATQ_OK;
+}
+
+int64_t atq_split_scaled_fused_max_elems(void) { return kFusedSplitMax; }
+
+int atq_split_scaled_fused(int device, const float* x, int64_t n, uint16_t* hi, uint16_t* lo, float bound_mul, const float* extra,
+                           float* slot, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && hi && slot && n > 0 && n <= kFusedSplitMax && (n % 8) == 0, "needs 0 < n <= max elems, n % 8 == 0");
+  ATQ_CHECK_ARG(aligned16(x) && aligned16(hi) && (lo == nullptr || aligned16(lo)), "needs 16-byte aligned contiguous tensors");
+  ATQ_CHECK_ARG(bound_mul > 0.f, "bound_mul must be positive");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (lo) split_scaled_cluster_kernel<true><<<kFusedCtas, kFusedThreads, 0, stream>>>(x, n >> 2, hi, lo, slot, bound_mul, extra);
+  else split_scaled_cluster_kernel<false><<<kFusedCtas, kFusedThreads, 0, stream>>>(x, n >> 2, hi, lo, slot, bound_mul, extra);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }

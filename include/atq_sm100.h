@@ -117,6 +117,16 @@ int atq_route_mask_mul(int device, const float* x, const float* grad_out, const 
  * (e.g. |dropout(gelu(y))| <= max|y| / (1-p)); extra is a nullable device scalar. */
 int atq_absmax_scale(int device, const float* x, int64_t rows, int64_t cols, int64_t ld, float bound_mul,
                      const float* extra, float* slot, atq_stream_t stream);
+/* the same reduction for `count` contiguous tensors in one launch (per-layer weight scales of a whole model) */
+int atq_absmax_scale_batched(int device, int count, const float* const* x_ptrs, const int64_t* ns,
+                             const float* const* extra_ptrs /* nullable */, float* const* slot_ptrs, float bound_mul,
+                             atq_stream_t stream);
+/* atq_absmax_scale + the scaled-fp16 split of a small contiguous tensor (n % 8 == 0, n <= max elems, 16-byte aligned)
+ * in ONE launch: a cluster of 8 CTAs holds the tensor in registers between the max|x| exchange (distributed shared
+ * memory) and the split.  Writes slot[1..2] = {s, 1/s}; slot[0], slot[3] untouched. */
+int64_t atq_split_scaled_fused_max_elems(void);
+int atq_split_scaled_fused(int device, const float* x, int64_t n, uint16_t* hi, uint16_t* lo, float bound_mul,
+                           const float* extra, float* slot, atq_stream_t stream);
 /* fp32 [rows, cols] (row pitch ld_in elements) -> hi (+ lo, nullable) [rows, pitch]; pitch % 8 == 0,
  * pitch >= cols; padding columns are left untouched. */
 int atq_split_bf16(int device, const float* x, int64_t rows, int64_t cols, int64_t ld_in,

@@ -70,8 +70,10 @@ def retrieval_forward_backward(model, manager, batch):
     feats = {}
     # the tensor the fp32 ResNet18 trunk hands to the ATQ part (models/multimodal_classifier.py:84-86): its gradient
     # is what the ternary projector's dX GEMM produces
-    hook = model.image_encoder.feature_norm.register_forward_pre_hook(
-        lambda mod, args: args[0].register_hook(lambda g: feats.__setitem__("dfeat", g.detach().cpu())))
+    def _tap(mod, args):
+        args[0].register_hook(lambda g: feats.__setitem__("dfeat", g.detach().cpu()))  # (returns None: input unchanged)
+
+    hook = model.image_encoder.feature_norm.register_forward_pre_hook(_tap)
     img, txt = model(images, captions, lengths, return_embeddings=True)
     hook.remove()
     loss = manager.compute_loss(img, txt)
