@@ -89,6 +89,11 @@ _SIGS = {
                                   _P, c_int, _P, c_int64, _P, _P]),
     "atq_attention_bwd": (c_int, [c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_float, c_float,
                                   _P, c_int, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P]),
+    "atq_rowkth_largest": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P]),
+    "atq_infonce_row_stats": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, c_float, _P, _P, _P, _P, _P]),
+    "atq_infonce_finalize": (c_int, [c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P]),
+    "atq_infonce_grad": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, c_float, _P, _P, _P, _P, _P, _P, c_float, c_float, _P,
+                                 _P, c_int64, _P, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

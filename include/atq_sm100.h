@@ -281,6 +281,29 @@ int atq_gated_residual_bwd(int device, const float* dout, const float* h, const 
 int atq_adamw_multi(int device, const void* table, const int* chunk_tensor, const int* chunk_off, int n_chunks, float lr,
                     float beta1, float beta2, float eps, float weight_decay, float* step, atq_stream_t stream);
 
+/* ---- fused hard-negative-mining InfoNCE (utils/enhanced_contrastive.py:64-158) -----------------
+ * s: [b, b] fp32 similarity / temperature (row pitch ld).  Hard negatives = entries at least as large as the k-th
+ * largest off-diagonal entry of their row or of their column (the two torch.topk calls of :98-110 + the mask loop of
+ * :118-120); W = s * (pw on the diagonal, hard_mul on hard negatives, 1 elsewhere).
+ *   atq_rowkth_largest      thr[i] = k-th largest of { s[i, j] : j != i }, exact (1 <= k <= b - 1; b <= 49 152)
+ *   atq_infonce_row_stats   per row of m (m = s with (thr_a, thr_b) = (row, col) thresholds, or m = s^T with them
+ *                           swapped): lse_w = logsumexp(W_i), lse_s = logsumexp(m_i), exp_s = sum softmax(m_i) m_i,
+ *                           wdiag (nullable) = W_ii
+ *   atq_infonce_finalize    loss = (CE_rows + CE_cols)/2 + lambda (H_rows + H_cols)/2 from the vectors above
+ *   atq_infonce_grad        ds = grad_out * out_scale * dL/ds for every entry; dpw (nullable) = dL/d pw            */
+int atq_rowkth_largest(int device, const float* s, int64_t b, int64_t ld, int64_t k, float* thr_out, atq_stream_t stream);
+int atq_infonce_row_stats(int device, const float* m, int64_t b, int64_t ld, const float* thr_a, const float* thr_b,
+                          const float* pw /* nullable */, float hard_mul, float* lse_w, float* lse_s, float* exp_s,
+                          float* wdiag /* nullable */, atq_stream_t stream);
+int atq_infonce_finalize(int device, int64_t b, const float* lse_w_r, const float* lse_w_c, const float* lse_s_r,
+                         const float* lse_s_c, const float* exp_s_r, const float* exp_s_c, const float* wdiag,
+                         float lambda_reg, float* loss, atq_stream_t stream);
+int atq_infonce_grad(int device, const float* s, int64_t b, int64_t ld, const float* thr_r, const float* thr_c,
+                     const float* pw /* nullable */, float hard_mul, const float* lse_w_r, const float* lse_w_c,
+                     const float* lse_s_r, const float* lse_s_c, const float* exp_s_r, const float* exp_s_c,
+                     float lambda_reg, float out_scale, const float* grad_out, float* ds, int64_t ld_out,
+                     float* dpw /* nullable */, atq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,19 +20,19 @@ def test_layers_under_autocast_and_grad_scaler():
     net = nn.Sequential(nn.Linear(64, 192), atq.ResidualPrecisionBoostLinear(192, 96, 0.2, True, 0.15), nn.GELU(),
                         atq.TernaryLinear(96, 32)).to(DEV)
     x = torch.randn(40, 64, device=DEV)
-    want = net(x).sum()
+    want = net(x).mean()
     want.backward()
     g_want = [p.grad.clone() for p in net.parameters() if p.grad is not None]
     net.zero_grad(set_to_none=True)
-    scaler = torch.amp.GradScaler("cuda")
+    scaler = torch.amp.GradScaler("cuda", init_scale=256.0)  # (the default 2^16 overflows the fp16 nn.Linear grads by design)
     with torch.autocast("cuda", dtype=torch.float16):
         y = net(x)   # nn.Linear hands fp16 activations to the ternary layers, exactly as the reference's attention does
         assert y.dtype == torch.float32, "ternary layers compute and return fp32 under autocast"
-        loss = y.sum()
+        loss = y.mean()
     scaler.scale(loss).backward()
     inv = 1.0 / scaler.get_scale()
     g_got = [p.grad * inv for p in net.parameters() if p.grad is not None]
-    assert abs(float(loss) - float(want)) <= 2e-2 * abs(float(want)) + 1e-1   # fp16 nn.Linear in front: loose
+    assert abs(float(loss) - float(want)) <= 2e-2 * abs(float(want)) + 1e-2   # fp16 nn.Linear in front: loose
     assert len(g_got) == len(g_want)
     for a, b in zip(g_got, g_want):
         assert torch.isfinite(a).all()
