@@ -60,13 +60,28 @@ class FlatGradAllReduce:
     outside `mask != 0` on every rank - ResidualPrecisionBoostLinear.weight with its `precision_mask`
     (dW = G .* mask, atq/precision_boost.py:72; the mask is identical on all ranks).  Only the masked
     entries travel: they are gathered into the flat buffer, reduced, and scattered back into the dense
-    `weight.grad` (whose other entries stay zero).  `rpb_masks(model)` builds the dictionary."""
+    `weight.grad` (whose other entries stay zero).  `rpb_masks(model)` builds the dictionary.
+
+    `overlap=True` (dense gradients only): the flat buffer is laid out in REVERSE parameter order and cut into buckets
+    of `bucket_bytes`; post-accumulate-grad hooks count the gradients of each bucket, and the moment a bucket is
+    complete its gradients are packed (one multi-tensor copy) and all-reduced on a communication stream while
+    autograd keeps running the rest of backward -- the bucketed, overlapped reduction of SURVEY section 5.  The comm
+    stream first waits for an event on every stream that produced a gradient of the bucket (the two towers of the
+    retrieval model run on different streams), `reduce()` launches whatever is left (parameters without a gradient
+    this step contribute zeros), joins the comm stream and re-points `p.grad` at the flat views.  Works eagerly and
+    under CUDA-graph capture (the comm stream becomes a branch of the captured graph).  The first step runs
+    un-overlapped: it discovers which parameters receive gradients."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 256 << 20, group=None,
-                 sparse_masks: Optional[dict] = None):
+                 sparse_masks: Optional[dict] = None, overlap: bool = False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
+        self.overlap = bool(overlap) and not sparse_masks
         self.bucket_elems = max(1, bucket_bytes // 4)
+        self._buckets: List[dict] = []       # overlap mode: {"lo", "hi", "idx": [active indices], "pending", "launched", "streams"}
+        self._bucket_of: dict = {}           # id(param) -> bucket number
+        self._hooks: list = []
+        self._comm = None
         self.flat: Optional[torch.Tensor] = None
         self.active: List[torch.nn.Parameter] = []
         self.views: List[torch.Tensor] = []
@@ -79,6 +94,8 @@ class FlatGradAllReduce:
 
     def _bind(self):
         self.active = [p for p in self.params if p.grad is not None]
+        if self.overlap:
+            self.active.reverse()  # gradients arrive roughly in reverse registration order: early buckets fill first
         self.sparse_idx = []
         for p in self.active:
             mask = self.sparse_masks.get(id(p))
@@ -101,13 +118,92 @@ class FlatGradAllReduce:
                 dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
                 self.views.append(piece.as_strided(p.size(), p.stride()) if dense else piece.view_as(p))
             off += (n + 3) // 4 * 4
+        if self.overlap:
+            self._make_buckets(sizes)
+
+    # ---- overlap mode ---------------------------------------------------------------------------------------
+    def _make_buckets(self, sizes):
+        for h in self._hooks:
+            h.remove()
+        self._hooks, self._buckets, self._bucket_of = [], [], {}
+        off, cur = 0, None
+        for i, (p, n) in enumerate(zip(self.active, sizes)):
+            padded = (n + 3) // 4 * 4
+            if cur is None or (off + padded - cur["lo"]) > self.bucket_elems and cur["idx"]:
+                cur = {"lo": off, "hi": off, "idx": [], "pending": 0, "launched": False, "streams": {}}
+                self._buckets.append(cur)
+            cur["idx"].append(i)
+            cur["hi"] = off + padded
+            self._bucket_of[id(p)] = len(self._buckets) - 1
+            off += padded
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        if self.flat.is_cuda:
+            self._comm = torch.cuda.Stream(device=self.flat.device)
+        self._arm()
+
+    def _arm(self):
+        for b in self._buckets:
+            b["pending"], b["launched"], b["streams"] = len(b["idx"]), False, {}
+
+    def _on_grad(self, p):
+        b = self._buckets[self._bucket_of[id(p)]]
+        if b["launched"]:
+            return  # a second accumulation into the same parameter (shared weights): reduce() handles it
+        if p.is_cuda:
+            st = torch.cuda.current_stream(p.device)
+            b["streams"][st.cuda_stream] = st
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        b["launched"] = True
+        dst, src = [], []
+        for i in b["idx"]:
+            p = self.active[i]
+            if p.grad is None:
+                self.views[i].zero_()
+            else:
+                dst.append(self.views[i])
+                src.append(p.grad)
+        piece = self.flat[b["lo"]: b["hi"]]
+        distributed = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        if self._comm is not None:
+            cur = torch.cuda.current_stream(self.flat.device)
+            b["streams"][cur.cuda_stream] = cur
+            for st in b["streams"].values():  # everything enqueued so far on the streams that produced these gradients
+                self._comm.wait_event(st.record_event())
+            with torch.cuda.stream(self._comm):
+                if dst:
+                    torch._foreach_copy_(dst, src)
+                if distributed:
+                    dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            if dst:
+                torch._foreach_copy_(dst, src)
+            if distributed:
+                dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _reduce_overlapped(self):
+        for b in self._buckets:
+            if not b["launched"]:
+                self._launch(b)
+        if self._comm is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._comm)
+        for p, view in zip(self.active, self.views):
+            p.grad = view
+        self._arm()
 
     def zero_grad(self):
         """Drop every gradient so autograd writes fresh tensors (no read-modify-write accumulation)."""
         for p in self.params:
             p.grad = None
+        if self._buckets:
+            self._arm()
 
     def reduce(self):
+        if self.overlap and self.flat is not None:
+            return self._reduce_overlapped()
         if self.flat is None or (self.sparse_masks and self._mask_versions != self._versions()):
             self._bind()  # first step (or a mask was re-initialised): discover the gradients this graph produces
         dst, grads = [], []

@@ -474,7 +474,8 @@ def measure_workload(args, cfg, steps, warmup, ctx, use_graph, clock_sampler=Non
     opt = T.make_optimizer(model, cfg, capturable=use_graph, fused=True, adamw_cls=None if args.torch_adamw else FlatAdamW)
     sync = None
     if world > 1:  # --sparse-grads: only the entries under each RPB precision_mask travel
-        sync = parallel.FlatGradAllReduce(model.parameters(), sparse_masks=parallel.rpb_masks(model) if args.sparse_grads else None)
+        sync = parallel.FlatGradAllReduce(model.parameters(), sparse_masks=parallel.rpb_masks(model) if args.sparse_grads else None,
+                                          overlap=not args.no_overlap_grads, bucket_bytes=args.bucket_mb << 20)
     gather = parallel.gather_embeddings if world > 1 else None
 
     pool = 4
@@ -634,6 +635,8 @@ def run_ours(args, cfg):
     if args.serial_towers:
         from workloads import models as WM
         WM.PARALLEL_TOWERS = False
+    if args.torch_loss:
+        T.FUSED_LOSS = False
     ctx = {"rank": rank, "world": world, "device": device, "peaks": load_peaks(), "flush": L2Flusher(device)}
     peaks = ctx["peaks"]
 
@@ -730,7 +733,10 @@ def main():
     ap.add_argument("--no-vitb16", action="store_true", help="skip the config-4 sub-run")
     ap.add_argument("--no-dropin", action="store_true", help="skip the reference-models-on-this-atq arm")
     ap.add_argument("--serial-towers", action="store_true", help="run the image and text towers on one stream (no graph branch concurrency)")
+    ap.add_argument("--torch-loss", action="store_true", help="contrastive loss as torch ops instead of the fused kernels")
     ap.add_argument("--torch-adamw", action="store_true", help="use torch.optim.AdamW(fused=True) instead of atq.optim.FlatAdamW")
+    ap.add_argument("--no-overlap-grads", action="store_true", help="N>1: one all-reduce after backward instead of overlapped buckets")
+    ap.add_argument("--bucket-mb", type=int, default=24, help="N>1: gradient bucket size of the overlapped all-reduce")
     ap.add_argument("--sparse-grads", action="store_true", help="N>1: all-reduce only the masked entries of RPB weight gradients")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -126,3 +126,48 @@ def test_sparse_rpb_gradient_all_reduce_matches_dense(tmp_path):
     a, b = (torch.load(tmp_path / f"s{r}.pt") for r in range(world))
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def _overlap_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from atq import parallel
+    parallel.init_from_env(backend="gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(12, 16), torch.nn.Tanh(), torch.nn.Linear(16, 9), torch.nn.Tanh(), torch.nn.Linear(9, 4))
+    unused = torch.nn.Linear(3, 3)
+    params = list(net.parameters()) + list(unused.parameters())
+    g = torch.Generator().manual_seed(7 + rank)
+    results = {}
+    for kind, sync in (("plain", parallel.FlatGradAllReduce(params)),
+                       ("overlap", parallel.FlatGradAllReduce(params, bucket_bytes=400, overlap=True))):
+        g.manual_seed(7 + rank)
+        for step in range(3):
+            x = torch.randn(5, 12, generator=g)
+            sync.zero_grad()
+            net(x).square().sum().backward()
+            sync.reduce()
+        results[kind] = [p.grad.clone() for p in net.parameters()]
+        if kind == "overlap":
+            assert len(sync._buckets) >= 3 and all(not b["launched"] for b in sync._buckets)  # re-armed for the next step
+            assert sync.active[0] is list(net.parameters())[-1]                                 # reverse layout
+    assert unused.weight.grad is None
+    for a, b in zip(results["plain"], results["overlap"]):
+        assert torch.equal(a, b)
+    torch.save(results["overlap"], os.path.join(out_dir, f"o{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucketed_all_reduce_matches_plain(tmp_path):
+    """Buckets launched from post-accumulate-grad hooks while backward is still running give the gradients of the
+    single flat all-reduce, on every rank."""
+    world = 2
+    mp.spawn(_overlap_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (torch.load(tmp_path / f"o{r}.pt") for r in range(world))
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

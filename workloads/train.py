@@ -15,6 +15,10 @@ import torch.nn.functional as F
 from . import models as M
 
 
+# True: configs built on the B200 `atq` use its fused contrastive loss; False: the torch-op restatement in models.py
+FUSED_LOSS = True
+
+
 @dataclass
 class RetrievalCfg:
     name: str
@@ -50,9 +54,14 @@ def build_retrieval(layers, cfg: RetrievalCfg, seed=42):
                              max_seq_length=cfg.seq_len,
                              vit_cfg=dict(embed_dim=cfg.embed_dim, depth=12, num_heads=12, dim_feedforward=cfg.hidden_dim,
                                           image_size=cfg.image_size) if cfg.image_tower == "vit" else None)
-    criterion = M.HardNegativeInfoNCE(temperature=0.07, lambda_reg=0.02, hard_negative_weight=0.5,
-                                      temperature_schedule=True)
-    manager = M.ContrastiveManager(criterion)
+    fused = getattr(layers, "HardNegativeMiningInfoNCE", None) if FUSED_LOSS else None
+    if fused is not None:  # the B200 package's fused loss (atq/contrastive.py); the CPU oracle namespace has none
+        criterion = fused(temperature=0.07, lambda_reg=0.02, hard_negative_weight=0.5, temperature_schedule=True)
+        manager = layers.ContrastiveLearningManager(None, criterion)
+    else:
+        criterion = M.HardNegativeInfoNCE(temperature=0.07, lambda_reg=0.02, hard_negative_weight=0.5,
+                                          temperature_schedule=True)
+        manager = M.ContrastiveManager(criterion)
     criterion.set_epoch(cfg.epoch, cfg.total_epochs)
     manager.set_epoch(cfg.epoch, cfg.total_epochs)
     return model, criterion, manager
