@@ -140,6 +140,42 @@ def ternarize_pack2(w: torch.Tensor, thr: torch.Tensor, stats: Optional[torch.Te
     return packed
 
 
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def _n_array(tensors):
+    return (ctypes.c_int64 * len(tensors))(*[t.numel() for t in tensors])
+
+
+def ternarize_pack2_batched(weights, thresholds):
+    """2-bit codec bytes of many layers in one launch (thresholds: [count] tensor or list of 0-dim tensors)."""
+    ws = [nv.require_f32(w, "weights") for w in weights]
+    dev = nv.device_index(ws[0])
+    packed = [torch.empty((w.numel() + 3) // 4, dtype=torch.uint8, device=w.device) for w in ws]
+    t_arr = (ctypes.c_void_p * len(ws))(*[thresholds[i].data_ptr() for i in range(len(ws))])
+    nv.call("atq_ternarize_pack2_batched", dev, len(ws), _ptr_array(ws), _n_array(ws), t_arr, _ptr_array(packed), nv.stream_ptr(dev))
+    return packed
+
+
+def pack2_from_f32_batched(tensors):
+    ts = [nv.require_f32(t, "ternary_weights") for t in tensors]
+    dev = nv.device_index(ts[0])
+    packed = [torch.empty((t.numel() + 3) // 4, dtype=torch.uint8, device=t.device) for t in ts]
+    flag = torch.zeros(1, dtype=torch.int32, device=ts[0].device)
+    nv.call("atq_pack2_from_f32_batched", dev, len(ts), _ptr_array(ts), _n_array(ts), _ptr_array(packed), flag.data_ptr(), nv.stream_ptr(dev))
+    return packed, flag
+
+
+def unpack2_batched(packed_list, numels):
+    dev = nv.device_index(packed_list[0])
+    outs = [torch.empty(n, dtype=torch.float32, device=p.device) for p, n in zip(packed_list, numels)]
+    flag = torch.zeros(1, dtype=torch.int32, device=packed_list[0].device)
+    n_arr = (ctypes.c_int64 * len(outs))(*[int(n) for n in numels])
+    nv.call("atq_unpack2_to_f32_batched", dev, len(outs), _ptr_array(packed_list), n_arr, _ptr_array(outs), flag.data_ptr(), nv.stream_ptr(dev))
+    return outs, flag
+
+
 def optimal_alpha(w: torch.Tensor, tern_stats: torch.Tensor) -> torch.Tensor:
     """alpha* of atq/quantizers.py:46-55 from the ternarize statistics (device-resolved branch)."""
     dev = nv.device_index(w)

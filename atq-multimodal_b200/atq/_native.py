@@ -52,6 +52,9 @@ _SIGS = {
     "atq_unpack2_to_f32": (c_int, [c_int, _P, c_int64, _P, _P, _P]),
     "atq_unpack2_to_bf16": (c_int, [c_int, _P, c_int64, _P, _P]),
     "atq_unpack2_to_i8": (c_int, [c_int, _P, c_int64, _P, _P]),
+    "atq_ternarize_pack2_batched": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), POINTER(c_void_p), _P]),
+    "atq_pack2_from_f32_batched": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), _P, _P]),
+    "atq_unpack2_to_f32_batched": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), _P, _P]),
     "atq_route_mask_mul": (c_int, [c_int, _P, _P, _P, c_int64, _P, _P]),
     "atq_absmax_scale": (c_int, [c_int, _P, c_int64, c_int64, c_int64, c_float, _P, _P, _P]),
     "atq_absmax_scale_batched": (c_int, [c_int, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), POINTER(c_void_p),

@@ -253,6 +253,101 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ------------------------------------------------------------------------------------
+// Codec kernels for whole models (BASELINE config 5: 1 B weights in ~60 layers): ONE launch for all layers
+// (blockIdx.y = layer, so no per-layer launch gap or tail), 128-bit global accesses on both sides.
+// A warp step covers 2048 consecutive weights: 16 coalesced float4 loads per lane (8 KB per warp in flight), the
+// 512 code bytes are transposed through a warp-private shared-memory strip, and every lane stores (or, for unpack,
+// loads) ONE 16-byte piece of the packed stream -- 64 weights per 128-bit packed access.
+// Layers must be 16-byte aligned; the last (n % 2048) weights of a layer take the scalar tail.
+// ------------------------------------------------------------------------------------
+constexpr int kCodecBatch = 64;
+enum { CODEC_TERNARIZE = 0, CODEC_PACK = 1, CODEC_UNPACK = 2 };
+struct CodecBatch {
+  const float* src[kCodecBatch];      // fp32 weights (TERNARIZE) / fp32 ternary values (PACK) / unused (UNPACK)
+  uint8_t* packed[kCodecBatch];       // 2-bit codes (written, or read for UNPACK)
+  float* dst[kCodecBatch];            // fp32 output (UNPACK)
+  const float* thr[kCodecBatch];      // per-layer threshold (TERNARIZE)
+  long long n[kCodecBatch];
+  int32_t* invalid_flag;              // PACK / UNPACK: set to 1 when a value / code is not ternary
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) codec_batched_kernel(const CodecBatch b) {
+  __shared__ __align__(16) uint8_t strip[kThreads / 32][512];
+  const int layer = blockIdx.y;
+  const long long n = b.n[layer];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long warps = (long long)gridDim.x * (kThreads / 32);
+  const long long wg = (long long)blockIdx.x * (kThreads / 32) + wid;
+  const long long chunks = n >> 11;  // 2048 weights per warp step
+  uint8_t* const my = strip[wid];
+  bool bad = false;
+  if constexpr (MODE != CODEC_UNPACK) {
+    const float* __restrict__ src = b.src[layer];
+    const float thr = (MODE == CODEC_TERNARIZE) ? __ldg(b.thr[layer]) : 0.f;
+    uint8_t* __restrict__ packed = b.packed[layer];
+    for (long long c = wg; c < chunks; c += warps) {
+      const float4* base = reinterpret_cast<const float4*>(src) + c * 512;
+      float4 v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = ldg_stream4(reinterpret_cast<const float*>(base + j * 32 + lane));
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        uint32_t c0, c1, c2, c3;
+        if constexpr (MODE == CODEC_TERNARIZE) {
+          c0 = tern_code(v[j].x, thr); c1 = tern_code(v[j].y, thr); c2 = tern_code(v[j].z, thr); c3 = tern_code(v[j].w, thr);
+        } else {
+          c0 = code_of<SRC_TERNARY>(v[j].x, 0.f, bad); c1 = code_of<SRC_TERNARY>(v[j].y, 0.f, bad);
+          c2 = code_of<SRC_TERNARY>(v[j].z, 0.f, bad); c3 = code_of<SRC_TERNARY>(v[j].w, 0.f, bad);
+        }
+        my[j * 32 + lane] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+      }
+      __syncwarp();
+      const uint4 out = *reinterpret_cast<const uint4*>(my + 16 * lane);
+      __syncwarp();
+      *reinterpret_cast<uint4*>(packed + c * 512 + 16 * lane) = out;
+    }
+    if (wg == 0 && lane == 0) {  // tail: whole bytes, then the ragged last byte (zero bits above the last code)
+      for (long long i = chunks << 11; i < n; i += 4) {
+        uint32_t byte = 0;
+        for (int j = 0; j < 4 && i + j < n; ++j) {
+          const float x = src[i + j];
+          const uint32_t code = (MODE == CODEC_TERNARIZE) ? tern_code(x, thr) : code_of<SRC_TERNARY>(x, 0.f, bad);
+          byte |= code << (2 * j);
+        }
+        packed[i >> 2] = (uint8_t)byte;
+      }
+    }
+  } else {
+    const uint8_t* __restrict__ packed = b.packed[layer];
+    float* __restrict__ dst = b.dst[layer];
+    for (long long c = wg; c < chunks; c += warps) {
+      *reinterpret_cast<uint4*>(my + 16 * lane) = __ldg(reinterpret_cast<const uint4*>(packed + c * 512) + lane);
+      __syncwarp();
+      float4* out = reinterpret_cast<float4*>(dst) + c * 512;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const uint32_t byte = my[j * 32 + lane];
+        const uint32_t c0 = byte & 3u, c1 = (byte >> 2) & 3u, c2 = (byte >> 4) & 3u, c3 = byte >> 6;
+        bad |= (c0 == 3u) | (c1 == 3u) | (c2 == 3u) | (c3 == 3u);
+        __stcs(out + j * 32 + lane, make_float4((float)c0 - 1.f, (float)c1 - 1.f, (float)c2 - 1.f, (float)c3 - 1.f));
+      }
+      __syncwarp();
+    }
+    if (wg == 0 && lane == 0) {
+      for (long long i = chunks << 11; i < n; ++i) {
+        const uint32_t code = ((uint32_t)packed[i >> 2] >> (2 * (int)(i & 3))) & 3u;
+        bad |= (code == 3u);
+        dst[i] = (float)code - 1.f;
+      }
+    }
+  }
+  if constexpr (MODE != CODEC_TERNARIZE) {
+    if (b.invalid_flag != nullptr && __any_sync(0xffffffffu, bad) && lane == 0) atomicExch(b.invalid_flag, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // K10: grad_in = grad_out * (|x| > thr)      (atq/routing.py:53-56)
 // ------------------------------------------------------------------------------------
 template <bool VEC>
@@ -1075,6 +1170,70 @@ int atq_unpack2_to_i8(int device, const uint8_t* packed, int64_t n, int8_t* out,
   ATQ_CHECK_ARG(packed && out && n > 0, "null pointer or n <= 0");
   ATQ_ENSURE_DEVICE(device);
   return launch_unpack<UNPACK_I8>(device, packed, n, out, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C" (the launcher below is a template)
+
+template <int MODE>
+static int codec_batched(int device, int count, const float* const* src, uint8_t* const* packed, float* const* dst,
+                         const float* const* thr, const int64_t* ns, int32_t* invalid_flag, cudaStream_t stream) {
+  for (int base = 0; base < count; base += kCodecBatch) {
+    const int m = count - base < kCodecBatch ? count - base : kCodecBatch;
+    CodecBatch b;
+    memset(&b, 0, sizeof(b));
+    int64_t nmax = 1;
+    for (int i = 0; i < m; ++i) {
+      const int k = base + i;
+      if (ns[k] <= 0 || packed[k] == nullptr || !aligned16(packed[k]) || (MODE != CODEC_UNPACK && (src[k] == nullptr || !aligned16(src[k]))) ||
+          (MODE == CODEC_UNPACK && (dst[k] == nullptr || !aligned16(dst[k]))) || (MODE == CODEC_TERNARIZE && thr[k] == nullptr)) {
+        set_error("batched codec: layer %d has a null / unaligned pointer or no elements", k);
+        return ATQ_EINVAL;
+      }
+      b.src[i] = MODE != CODEC_UNPACK ? src[k] : nullptr;
+      b.packed[i] = packed[k];
+      b.dst[i] = MODE == CODEC_UNPACK ? dst[k] : nullptr;
+      b.thr[i] = MODE == CODEC_TERNARIZE ? thr[k] : nullptr;
+      b.n[i] = ns[k];
+      if (ns[k] > nmax) nmax = ns[k];
+    }
+    b.invalid_flag = invalid_flag;
+    // CTAs per layer: enough for the largest layer, the whole grid a few waves of the machine
+    int64_t per = ((nmax >> 11) + (kThreads / 32) - 1) / (kThreads / 32);
+    const int64_t cap = ((int64_t)sm_count(device) * 8 + m - 1) / m;
+    if (per > cap) per = cap;
+    if (per < 1) per = 1;
+    codec_batched_kernel<MODE><<<dim3((unsigned)per, (unsigned)m), kThreads, 0, stream>>>(b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("batched codec launch failed: %s", cudaGetErrorString(e));
+      return ATQ_ECUDA;
+    }
+    note_launch();
+  }
+  return ATQ_OK;
+}
+
+extern "C" {
+
+int atq_ternarize_pack2_batched(int device, int count, const float* const* w_ptrs, const int64_t* ns, const float* const* thr_ptrs,
+                                uint8_t* const* packed_ptrs, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(count > 0 && w_ptrs && ns && thr_ptrs && packed_ptrs, "null pointer or count <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return codec_batched<CODEC_TERNARIZE>(device, count, w_ptrs, packed_ptrs, nullptr, thr_ptrs, ns, nullptr, (cudaStream_t)stream_);
+}
+
+int atq_pack2_from_f32_batched(int device, int count, const float* const* t_ptrs, const int64_t* ns, uint8_t* const* packed_ptrs,
+                               int32_t* invalid_flag, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(count > 0 && t_ptrs && ns && packed_ptrs, "null pointer or count <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return codec_batched<CODEC_PACK>(device, count, t_ptrs, packed_ptrs, nullptr, nullptr, ns, invalid_flag, (cudaStream_t)stream_);
+}
+
+int atq_unpack2_to_f32_batched(int device, int count, uint8_t* const* packed_ptrs, const int64_t* ns, float* const* out_ptrs,
+                               int32_t* invalid_flag, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(count > 0 && packed_ptrs && ns && out_ptrs, "null pointer or count <= 0");
+  ATQ_ENSURE_DEVICE(device);
+  return codec_batched<CODEC_UNPACK>(device, count, nullptr, packed_ptrs, out_ptrs, nullptr, ns, invalid_flag, (cudaStream_t)stream_);
 }
 
 int atq_route_mask_mul(int device, const float* x, const float* grad_out, const float* thr, int64_t n, float* grad_in,

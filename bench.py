@@ -394,7 +394,7 @@ def streaming_rooflines(device, peaks, flush):
 
     def quantize_pack():
         th = eng.adaptive_threshold_batched(ws, ss)
-        return [eng.ternarize_pack2(t, th[i]) for i, t in enumerate(ws)]
+        return eng.ternarize_pack2_batched(ws, th)     # one launch for all layers
 
     packed = quantize_pack()
     rec("threshold, batched over layers", wl, 4.0, total, _event_time(lambda: eng.adaptive_threshold_batched(ws, ss), 3, flush))
@@ -402,10 +402,13 @@ def streaming_rooflines(device, peaks, flush):
     rec("quantize+pack (threshold + ternarize -> 2-bit)", wl, 8.25, total, ms_qp, None,
         "two-read bound 8.25 B/elem (one read for the order statistic, one for ternarize); single-read bound 4.25 -> "
         f"{round(4.25 * total / (ms_qp * 1e-3) / 1e9 / hbm, 4)} of peak")
-    rec("unpack 2-bit -> fp32", wl, 4.25, total, _event_time(lambda: [eng.unpack2(p, t.numel()) for p, t in zip(packed, ws)], 3, flush))
-    tern = [eng.unpack2(p, t.numel()) for p, t in zip(packed, ws)]
+    numels = [t.numel() for t in ws]
+    th = eng.adaptive_threshold_batched(ws, ss)
+    rec("ternarize -> 2-bit, batched over layers", wl, 4.25, total, _event_time(lambda: eng.ternarize_pack2_batched(ws, th), 3, flush))
+    rec("unpack 2-bit -> fp32", wl, 4.25, total, _event_time(lambda: eng.unpack2_batched(packed, numels), 3, flush))
+    tern, _ = eng.unpack2_batched(packed, numels)
     del ws
-    rec("pack fp32 ternary -> 2-bit", wl, 4.25, total, _event_time(lambda: [eng.pack2_from_f32(t)[0] for t in tern], 3, flush))
+    rec("pack fp32 ternary -> 2-bit", wl, 4.25, total, _event_time(lambda: eng.pack2_from_f32_batched(tern), 3, flush))
     out.append({"kernel": "quantize+pack throughput", "workload": wl, "gelem_per_s": round(total / ms_qp / 1e6, 1)})
     del tern, packed
     torch.cuda.empty_cache()

@@ -100,6 +100,16 @@ int atq_unpack2_to_f32(int device, const uint8_t* packed, int64_t n, float* out,
 int atq_unpack2_to_bf16(int device, const uint8_t* packed, int64_t n, uint16_t* out, atq_stream_t stream);
 int atq_unpack2_to_i8(int device, const uint8_t* packed, int64_t n, int8_t* out, atq_stream_t stream);
 
+/* Whole-model forms of the three codec kernels (BASELINE config 5: ~1 B weights in tens of layers): one launch for
+ * all layers, 64 weights per 128-bit packed access, 16-byte aligned layers; bytes identical to the per-layer calls.
+ * invalid_flag (nullable) is set to 1 if any value is not in {-1, 0, +1} (pack) / any code is 3 (unpack). */
+int atq_ternarize_pack2_batched(int device, int count, const float* const* w_ptrs, const int64_t* ns,
+                                const float* const* thr_ptrs, uint8_t* const* packed_ptrs, atq_stream_t stream);
+int atq_pack2_from_f32_batched(int device, int count, const float* const* t_ptrs, const int64_t* ns,
+                               uint8_t* const* packed_ptrs, int32_t* invalid_flag, atq_stream_t stream);
+int atq_unpack2_to_f32_batched(int device, int count, uint8_t* const* packed_ptrs, const int64_t* ns,
+                               float* const* out_ptrs, int32_t* invalid_flag, atq_stream_t stream);
+
 /* ---- D2: selective gradient routing backward (atq/routing.py:53-56) ------------------ */
 /* grad_in = grad_out * (|x| > *thr) */
 int atq_route_mask_mul(int device, const float* x, const float* grad_out, const float* thr, int64_t n,

@@ -246,3 +246,34 @@ def test_sampled_select_large_layers_bit_exact(kind):
     assert float(thr[3]) == float(eng.adaptive_threshold(small, 0.1))
     km = int(0.2 * medium.numel())
     assert np.float32(thr[2].item()).tobytes() == np.float32(np.partition(a[: medium.numel()], km)[km]).tobytes()
+
+
+def test_batched_codec_matches_per_layer_and_oracle():
+    """Whole-model codec kernels (one launch, 128-bit packed accesses): bytes identical to the per-layer kernels and
+    to the oracle for ragged layer sizes (tails shorter than a 2048-weight warp step, n % 4 != 0)."""
+    g = torch.Generator().manual_seed(11)
+    shapes = [(4096, 512), (300, 77), (1, 96), (2050, 1), (64, 64), (5, 5), (1, 1), (1000, 2049)]
+    ws = [((torch.rand(*s, generator=g) * 2 - 1) / 8).to(DEV) for s in shapes]
+    ss = [0.05, 0.3, 0.2, 0.5, 0.13125, 0.4, 0.3, 0.25]
+    thr = eng.adaptive_threshold_batched(ws, ss)
+    packed = eng.ternarize_pack2_batched(ws, thr)
+    for w, s, p, t in zip(ws, ss, packed, thr):
+        want = eng.ternarize_pack2(w, t)
+        assert torch.equal(p, want)
+        t_ref, _, _ = O.adaptive_ternary_quantization(w.cpu().numpy(), None, 0.05, s)
+        assert np.array_equal(p.cpu().numpy(), O.pack2(t_ref))
+    outs, flag = eng.unpack2_batched(packed, [w.numel() for w in ws])
+    assert int(flag) == 0
+    for w, p, o in zip(ws, packed, outs):
+        assert torch.equal(o, eng.unpack2(p, w.numel()))
+    repacked, flag = eng.pack2_from_f32_batched(outs)
+    assert int(flag) == 0 and all(torch.equal(a, b) for a, b in zip(repacked, packed))
+    # validation flags: a non-ternary value / a code 3 anywhere in the batch
+    bad = [o.clone() for o in outs]
+    bad[3][7] = 0.5
+    _, flag = eng.pack2_from_f32_batched(bad)
+    assert int(flag) == 1
+    badp = [p.clone() for p in packed]
+    badp[0][123] = 0xFF
+    _, flag = eng.unpack2_batched(badp, [w.numel() for w in ws])
+    assert int(flag) == 1
