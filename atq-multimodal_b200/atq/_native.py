@@ -88,9 +88,9 @@ _SIGS = {
     "atq_gated_residual_fwd": (c_int, [c_int, _P, _P, _P, c_int64, c_float, _P, _P, _P]),
     "atq_gated_residual_bwd": (c_int, [c_int, _P, _P, _P, c_int64, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "atq_adamw_multi": (c_int, [c_int, _P, _P, _P, c_int, c_float, c_float, c_float, c_float, c_float, _P, _P]),
-    "atq_attention_fwd": (c_int, [c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_float, c_float,
+    "atq_attention_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_float, c_float,
                                   _P, c_int, _P, c_int64, _P, _P]),
-    "atq_attention_bwd": (c_int, [c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_float, c_float,
+    "atq_attention_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_float, c_float,
                                   _P, c_int, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P]),
     "atq_rowkth_largest": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P]),
     "atq_infonce_row_stats": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, c_float, _P, _P, _P, _P, _P]),

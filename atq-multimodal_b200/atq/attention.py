@@ -20,12 +20,13 @@ import torch
 from . import _engine as eng
 from . import _native as nv
 
-HEAD_DIM = 64
+HEAD_DIM = 64   # tile width: head dims that are a multiple of 8 up to 64 are supported (narrower heads are zero-padded in shared memory)
 MAX_LEN = 256
 
 
 def supported(embed_dim: int, num_heads: int, seq_len: int) -> bool:
-    return embed_dim == num_heads * HEAD_DIM and 1 <= seq_len <= MAX_LEN
+    hd = embed_dim // max(num_heads, 1)
+    return embed_dim == num_heads * hd and hd % 8 == 0 and 8 <= hd <= HEAD_DIM and 1 <= seq_len <= MAX_LEN
 
 
 def _rows(t: torch.Tensor, name: str):
@@ -55,12 +56,12 @@ class _AttentionCoreFn(torch.autograd.Function):
         if k.shape != q.shape or v.shape != q.shape:
             raise RuntimeError("atq.attention: q, k, v must have the same [B, L, E] shape (self-attention)")
         if not supported(e, num_heads, l):
-            raise RuntimeError(f"atq.attention: unsupported shape E={e} heads={num_heads} L={l} (head_dim 64, L <= 256)")
+            raise RuntimeError(f"atq.attention: unsupported shape E={e} heads={num_heads} L={l} (head_dim % 8 == 0, <= 64; L <= 256)")
         dev = nv.device_index(q)
         out = torch.empty((b, l, e), dtype=torch.float32, device=q.device)
         lse = torch.empty((b * num_heads, l), dtype=torch.float32, device=q.device)
         terms = _terms()
-        nv.call("atq_attention_fwd", dev, b, num_heads, l, q.data_ptr(), qp, k.data_ptr(), kp, v.data_ptr(), vp,
+        nv.call("atq_attention_fwd", dev, b, num_heads, l, e // num_heads, q.data_ptr(), qp, k.data_ptr(), kp, v.data_ptr(), vp,
                 nv.ptr(key_padding), float(scale), float(dropout_p), nv.ptr(seed), terms, out.data_ptr(), e,
                 lse.data_ptr(), nv.stream_ptr(dev))
         ctx.save_for_backward(q, k, v, out, lse, key_padding, seed)
@@ -78,7 +79,7 @@ class _AttentionCoreFn(torch.autograd.Function):
         dq = torch.empty((b, l, e), dtype=torch.float32, device=q.device)
         dk = torch.empty_like(dq)
         dv = torch.empty_like(dq)
-        nv.call("atq_attention_bwd", dev, b, num_heads, l, q.data_ptr(), qp, k.data_ptr(), kp, v.data_ptr(), vp,
+        nv.call("atq_attention_bwd", dev, b, num_heads, l, e // num_heads, q.data_ptr(), qp, k.data_ptr(), kp, v.data_ptr(), vp,
                 nv.ptr(key_padding), scale, dropout_p, nv.ptr(seed), terms, out.data_ptr(), e, dout.data_ptr(), dop,
                 lse.data_ptr(), dq.data_ptr(), e, dk.data_ptr(), e, dv.data_ptr(), e, nv.stream_ptr(dev))
         return dq, dk, dv, None, None, None, None, None
@@ -91,7 +92,7 @@ def attention_core(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, num_heads:
     Returns [B, L, E].  `seed` (int64 CUDA tensor [1]) pins the dropout mask; by default one is drawn from
     torch's CUDA generator (so `torch.manual_seed` governs it and CUDA-graph replays advance it)."""
     if scale is None:
-        scale = 1.0 / math.sqrt(HEAD_DIM)
+        scale = 1.0 / math.sqrt(q.shape[-1] // int(num_heads))
     if scale <= 0:
         raise RuntimeError("atq.attention: scale must be positive")
     p = float(dropout_p) if training else 0.0

@@ -1,6 +1,7 @@
 // Fused attention core for the ternary transformer blocks:
 //
-//   O = dropout(softmax(scale * Q K^T + key_padding_mask)) V        per (batch, head), head_dim 64
+//   O = dropout(softmax(scale * Q K^T + key_padding_mask)) V        per (batch, head), head_dim <= 64 (multiple of 8;
+//   the tiles are 64 wide: the missing columns of a smaller head are staged as zeros and never stored)
 //
 // replaces the reference's explicit matmul / masked_fill / softmax / dropout / matmul sequence
 // (models/text_encoder.py:117-163, TernaryMultiheadAttention._scaled_dot_product_attention) and its
@@ -30,6 +31,7 @@ constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
 struct AttnParams {
   const float *q, *k, *v;
   int64_t q_pitch, k_pitch, v_pitch;
+  int hd;  // real head dim (<= 64, multiple of 8); tiles are 64 wide, columns >= hd are staged as zeros and never stored
   const uint8_t* key_pad;  // [B, L], non-zero = padded key; nullable
   float* out;
   int64_t out_pitch;
@@ -80,8 +82,9 @@ __device__ __forceinline__ void convert_store_row(const float4& a, const float4&
 
 template <bool LO, int PASSES = 4>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t pitch, int rows_valid, int rows_total,
-                                           uint32_t s_hi, uint32_t s_lo) {
+                                           uint32_t s_hi, uint32_t s_lo, int hd) {
   const int c = threadIdx.x & 7;
+  if (8 * c >= hd) rows_valid = 0;  // head dims < 64: the missing 8-column chunks are zero padding
   constexpr int kRowsPerPass = kAttThreads / 8;  // 32
   for (int r0 = threadIdx.x >> 3; r0 < rows_total; r0 += PASSES * kRowsPerPass) {
     float4 a[PASSES], b[PASSES];
@@ -109,8 +112,9 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_
 template <bool LO>
 __device__ __forceinline__ void stage_two_tiles(const float* __restrict__ src0, int64_t pitch0, uint32_t s_hi0, uint32_t s_lo0,
                                                 const float* __restrict__ src1, int64_t pitch1, uint32_t s_hi1, uint32_t s_lo1,
-                                                int rows_valid) {
+                                                int rows_valid, int hd) {
   const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+  if (8 * c >= hd) rows_valid = 0;
   float4 a0[4], b0[4], a1[4], b1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -221,14 +225,14 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   }
   if (warp == 0) tmem_alloc<512>(smem_u32(&s_tmem));
   build_valid_bits(p, b, s_valid);
-  const float* kg = p.k + (int64_t)b * L * p.k_pitch + h * kHd;
-  const float* vg = p.v + (int64_t)b * L * p.v_pitch + h * kHd;
+  const float* kg = p.k + (int64_t)b * L * p.k_pitch + h * p.hd;
+  const float* vg = p.v + (int64_t)b * L * p.v_pitch + h * p.hd;
   if (lo) {
-    stage_tile<true, 8>(kg, p.k_pitch, L, NK, s_kh, s_kl);
-    stage_tile<true, 8>(vg, p.v_pitch, L, NK, s_vh, s_vl);
+    stage_tile<true, 8>(kg, p.k_pitch, L, NK, s_kh, s_kl, p.hd);
+    stage_tile<true, 8>(vg, p.v_pitch, L, NK, s_vh, s_vl, p.hd);
   } else {
-    stage_tile<false, 8>(kg, p.k_pitch, L, NK, s_kh, 0);
-    stage_tile<false, 8>(vg, p.v_pitch, L, NK, s_vh, 0);
+    stage_tile<false, 8>(kg, p.k_pitch, L, NK, s_kh, 0, p.hd);
+    stage_tile<false, 8>(vg, p.v_pitch, L, NK, s_vh, 0, p.hd);
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -244,9 +248,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
 
   for (int q0 = 0; q0 < L; q0 += 128) {
     const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
-    const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * kHd;
-    if (lo) stage_tile<true>(qg, p.q_pitch, q_valid, 128, s_qh, s_ql);
-    else stage_tile<false>(qg, p.q_pitch, q_valid, 128, s_qh, 0);
+    const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * p.hd;
+    if (lo) stage_tile<true>(qg, p.q_pitch, q_valid, 128, s_qh, s_ql, p.hd);
+    else stage_tile<false>(qg, p.q_pitch, q_valid, 128, s_qh, 0, p.hd);
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
@@ -377,9 +381,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       float o[32];
       ld_row32(t_o + lane_off + (uint32_t)(half * 32), o);
       if (q < L) {
-        float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)b * L + q) * p.out_pitch + h * kHd + half * 32);
+        float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)b * L + q) * p.out_pitch + h * p.hd + half * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
+        for (int j = 0; j < 8; ++j)
+          if (half * 32 + 4 * j < p.hd) dst[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
       }
     }
     if (half == 0 && q < L && p.lse != nullptr) p.lse[(int64_t)bh * L + q] = sum > 0.f ? m * p.scale + logf(sum) : -INFINITY;
@@ -434,28 +439,31 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
 
   for (int k0 = 0; k0 < L; k0 += 128) {
     const int k_valid = (L - k0) < 128 ? (L - k0) : 128;
-    const float* kg = p.k + ((int64_t)b * L + k0) * p.k_pitch + h * kHd;
-    const float* vg = p.v + ((int64_t)b * L + k0) * p.v_pitch + h * kHd;
-    if (lo) stage_two_tiles<true>(kg, p.k_pitch, s_kh, s_kl, vg, p.v_pitch, s_vh, s_vl, k_valid);
-    else stage_two_tiles<false>(kg, p.k_pitch, s_kh, 0, vg, p.v_pitch, s_vh, 0, k_valid);
+    const float* kg = p.k + ((int64_t)b * L + k0) * p.k_pitch + h * p.hd;
+    const float* vg = p.v + ((int64_t)b * L + k0) * p.v_pitch + h * p.hd;
+    if (lo) stage_two_tiles<true>(kg, p.k_pitch, s_kh, s_kl, vg, p.v_pitch, s_vh, s_vl, k_valid, p.hd);
+    else stage_two_tiles<false>(kg, p.k_pitch, s_kh, 0, vg, p.v_pitch, s_vh, 0, k_valid, p.hd);
     for (int q0 = 0; q0 < L; q0 += 128) {
       const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
-      const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * kHd;
-      const float* dg = p.dout + ((int64_t)b * L + q0) * p.do_pitch + h * kHd;
+      const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * p.hd;
+      const float* dg = p.dout + ((int64_t)b * L + q0) * p.do_pitch + h * p.hd;
       // delta = sum_d dO[q,d] * O[q,d] over this head (row-sum of P .* dP): each column half adds 32 columns.
       // Its loads are issued before the tile staging so that their latency hides behind the conversions.
       const int q = q0 + row;
       const bool q_ok = q < L;
       float4 dx[8], dy[8];
       if (q_ok) {
-        const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * kHd + half * 32);
-        const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * kHd + half * 32);
+        const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * p.hd + half * 32);
+        const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * p.hd + half * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { dx[j] = __ldg(po + j); dy[j] = __ldg(pd + j); }
+        for (int j = 0; j < 8; ++j) {
+          if (half * 32 + 4 * j < p.hd) { dx[j] = __ldg(po + j); dy[j] = __ldg(pd + j); }
+          else { dx[j] = make_float4(0.f, 0.f, 0.f, 0.f); dy[j] = dx[j]; }
+        }
       }
       const float lse_q = q_ok ? __ldg(p.lse + (int64_t)bh * L + q) : 0.f;
-      if (lo) stage_two_tiles<true>(qg, p.q_pitch, s_qh, s_ql, dg, p.do_pitch, s_dh, s_dl, q_valid);
-      else stage_two_tiles<false>(qg, p.q_pitch, s_qh, 0, dg, p.do_pitch, s_dh, 0, q_valid);
+      if (lo) stage_two_tiles<true>(qg, p.q_pitch, s_qh, s_ql, dg, p.do_pitch, s_dh, s_dl, q_valid, p.hd);
+      else stage_two_tiles<false>(qg, p.q_pitch, s_qh, 0, dg, p.do_pitch, s_dh, 0, q_valid, p.hd);
       {
         float d = 0.f;
         if (q_ok) {
@@ -580,9 +588,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         float g[32];
         ld_row32(t_dq + lane_off + (uint32_t)(half * 32), g);
         if (q_ok) {
-          float4* dst = reinterpret_cast<float4*>(p.dq + ((int64_t)b * L + q) * p.dq_pitch + h * kHd + half * 32);
+          float4* dst = reinterpret_cast<float4*>(p.dq + ((int64_t)b * L + q) * p.dq_pitch + h * p.hd + half * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            if (half * 32 + 4 * j >= p.hd) continue;
             float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
             if (k0 > 0) {
               const float4 old = dst[j];
@@ -631,9 +640,10 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
       float g[32];
       ld_row32((which ? t_dv : t_dk) + lane_off + (uint32_t)(half * 32), g);
       if (kk < L) {
-        float4* dst = reinterpret_cast<float4*>(dstbase + ((int64_t)b * L + kk) * pitch + h * kHd + half * 32);
+        float4* dst = reinterpret_cast<float4*>(dstbase + ((int64_t)b * L + kk) * pitch + h * p.hd + half * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+        for (int j = 0; j < 8; ++j)
+          if (half * 32 + 4 * j < p.hd) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
       }
     }
     tcgen05_fence_before();
@@ -651,7 +661,7 @@ static int check_attn_ptr(const void* ptr, int64_t pitch, const char* name) {
   return ATQ_OK;
 }
 
-static int fill_common(AttnParams& p, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+static int fill_common(AttnParams& p, int B, int H, int L, int head_dim, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
                        const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
                        const unsigned long long* seed, int terms) {
   if (B <= 0 || H <= 0 || L <= 0 || L > 256) {
@@ -666,9 +676,13 @@ static int fill_common(AttnParams& p, int B, int H, int L, const float* q, int64
     set_error("atq_attention: dropout_p must be in [0, 1)");
     return ATQ_EINVAL;
   }
-  const int64_t width = (int64_t)H * kHd;
+  if (head_dim < 8 || head_dim > kHd || (head_dim % 8) != 0) {
+    set_error("atq_attention: head_dim must be a multiple of 8 in [8, 64] (got %d)", head_dim);
+    return ATQ_EINVAL;
+  }
+  const int64_t width = (int64_t)H * head_dim;
   if (q_pitch < width || k_pitch < width || v_pitch < width) {
-    set_error("atq_attention: row pitch smaller than H * 64");
+    set_error("atq_attention: row pitch smaller than H * head_dim");
     return ATQ_EINVAL;
   }
   int r;
@@ -680,6 +694,7 @@ static int fill_common(AttnParams& p, int B, int H, int L, const float* q, int64
   p.q_pitch = q_pitch; p.k_pitch = k_pitch; p.v_pitch = v_pitch;
   p.key_pad = key_padding;
   p.B = B; p.H = H; p.L = L;
+  p.hd = head_dim;
   p.scale = scale;
   p.terms = terms;
   p.seed = seed;
@@ -693,15 +708,15 @@ using namespace atq;
 
 extern "C" {
 
-int atq_attention_fwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+int atq_attention_fwd(int device, int B, int H, int L, int head_dim, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
                       const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
                       const unsigned long long* seed, int terms, float* out, int64_t out_pitch, float* lse,
                       atq_stream_t stream_) {
   AttnParams p;
   int r;
-  if ((r = fill_common(p, B, H, L, q, q_pitch, k, k_pitch, v, v_pitch, key_padding, scale, dropout_p, seed, terms)) != ATQ_OK) return r;
+  if ((r = fill_common(p, B, H, L, head_dim, q, q_pitch, k, k_pitch, v, v_pitch, key_padding, scale, dropout_p, seed, terms)) != ATQ_OK) return r;
   if ((r = check_attn_ptr(out, out_pitch, "out")) != ATQ_OK) return r;
-  ATQ_CHECK_ARG(out_pitch >= (int64_t)H * kHd, "out pitch smaller than H * 64");
+  ATQ_CHECK_ARG(out_pitch >= (int64_t)H * head_dim, "out pitch smaller than H * head_dim");
   ATQ_ENSURE_DEVICE(device);
   p.out = out; p.out_pitch = out_pitch; p.lse = lse;
   p.NK = (L + 31) / 32 * 32;
@@ -726,23 +741,23 @@ int atq_attention_fwd(int device, int B, int H, int L, const float* q, int64_t q
   return ATQ_OK;
 }
 
-int atq_attention_bwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+int atq_attention_bwd(int device, int B, int H, int L, int head_dim, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
                       const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
                       const unsigned long long* seed, int terms, const float* out, int64_t out_pitch, const float* dout,
                       int64_t dout_pitch, const float* lse, float* dq, int64_t dq_pitch, float* dk, int64_t dk_pitch,
                       float* dv, int64_t dv_pitch, atq_stream_t stream_) {
   AttnParams p;
   int r;
-  if ((r = fill_common(p, B, H, L, q, q_pitch, k, k_pitch, v, v_pitch, key_padding, scale, dropout_p, seed, terms)) != ATQ_OK) return r;
+  if ((r = fill_common(p, B, H, L, head_dim, q, q_pitch, k, k_pitch, v, v_pitch, key_padding, scale, dropout_p, seed, terms)) != ATQ_OK) return r;
   if ((r = check_attn_ptr(out, out_pitch, "out")) != ATQ_OK) return r;
   if ((r = check_attn_ptr(dout, dout_pitch, "dout")) != ATQ_OK) return r;
   if ((r = check_attn_ptr(dq, dq_pitch, "dq")) != ATQ_OK) return r;
   if ((r = check_attn_ptr(dk, dk_pitch, "dk")) != ATQ_OK) return r;
   if ((r = check_attn_ptr(dv, dv_pitch, "dv")) != ATQ_OK) return r;
   ATQ_CHECK_ARG(lse != nullptr, "lse is null");
-  const int64_t width = (int64_t)H * kHd;
+  const int64_t width = (int64_t)H * head_dim;
   ATQ_CHECK_ARG(out_pitch >= width && dout_pitch >= width && dq_pitch >= width && dk_pitch >= width && dv_pitch >= width,
-                "row pitch smaller than H * 64");
+                "row pitch smaller than H * head_dim");
   ATQ_ENSURE_DEVICE(device);
   p.o = out; p.o_pitch = out_pitch; p.dout = dout; p.do_pitch = dout_pitch;
   p.lse = const_cast<float*>(lse);

@@ -250,11 +250,11 @@ int atq_colsum_f32(int device, const float* x, int64_t rows, int64_t cols, int64
  * lse: [B*H, L] log-sum-exp of the scaled masked scores (forward output, backward input).
  * seed: device scalar (nullable = 0) for the counter-based dropout hash; the backward call must pass
  * the same seed / dropout_p.  terms: 3 = bf16 hi/lo operand split (parity), 1 = bf16 (fast). */
-int atq_attention_fwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+int atq_attention_fwd(int device, int B, int H, int L, int head_dim /* multiple of 8, <= 64 */, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
                       const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
                       const unsigned long long* seed, int terms, float* out, int64_t out_pitch, float* lse,
                       atq_stream_t stream);
-int atq_attention_bwd(int device, int B, int H, int L, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
+int atq_attention_bwd(int device, int B, int H, int L, int head_dim, const float* q, int64_t q_pitch, const float* k, int64_t k_pitch,
                       const float* v, int64_t v_pitch, const uint8_t* key_padding, float scale, float dropout_p,
                       const unsigned long long* seed, int terms, const float* out, int64_t out_pitch, const float* dout,
                       int64_t dout_pitch, const float* lse, float* dq, int64_t dq_pitch, float* dk, int64_t dk_pitch,

@@ -28,11 +28,11 @@ def _reference(q, k, v, heads, pad, scale, keep, p):
     return (pr @ vh).transpose(1, 2).reshape(b, l, e)
 
 
-def _run_case(b, heads, l, p, with_pad, mode, tol):
+def _run_case(b, heads, l, p, with_pad, mode, tol, hd=64):
     atq.set_gemm_mode(mode)
     try:
         g = torch.Generator().manual_seed(b * 1000 + heads * 100 + l)
-        e = heads * 64
+        e = heads * hd
         q, k, v = (torch.randn(b, l, e, generator=g) for _ in range(3))
         dout = torch.randn(b, l, e, generator=g)
         pad = None
@@ -41,7 +41,7 @@ def _run_case(b, heads, l, p, with_pad, mode, tol):
             pad = torch.arange(l)[None, :] >= lens[:, None]
         seed_val = 1234567891011 + l
         seed = torch.tensor([seed_val], dtype=torch.int64, device=DEV)
-        scale = 1.0 / math.sqrt(64)
+        scale = 1.0 / math.sqrt(hd)
         qg, kg, vg = (t.to(DEV).requires_grad_(True) for t in (q, k, v))
         out = A.attention_core(qg, kg, vg, heads, None if pad is None else pad.to(DEV), scale, p, True, seed=seed)
         out.backward(dout.to(DEV))
@@ -67,6 +67,13 @@ def _run_case(b, heads, l, p, with_pad, mode, tol):
     (2, 1, 256, 0.0, True), (2, 2, 1, 0.0, False), (1, 2, 33, 0.25, True), (2, 2, 128, 0.0, False), (1, 1, 129, 0.1, True)])
 def test_attention_core_parity_mode(b, heads, l, p, with_pad):
     _run_case(b, heads, l, p, with_pad, "parity", dict(rtol=1e-2, atol=1e-3))
+
+
+@pytest.mark.parametrize("hd,b,heads,l,p,with_pad", [(24, 16, 8, 50, 0.1, True), (24, 2, 8, 50, 0.0, False), (32, 2, 4, 197, 0.1, True),
+                                                      (8, 1, 3, 17, 0.0, False), (48, 2, 2, 256, 0.0, True), (56, 1, 2, 130, 0.1, False)])
+def test_attention_core_narrow_heads(hd, b, heads, l, p, with_pad):
+    """head_dim < 64 (BASELINE config 2: embed 192 / 8 heads = 24): zero-padded 64-wide tiles, same tolerance."""
+    _run_case(b, heads, l, p, with_pad, "parity", dict(rtol=1e-2, atol=1e-3), hd=hd)
 
 
 @pytest.mark.parametrize("b,heads,l,p,with_pad", [(2, 2, 50, 0.0, True), (1, 3, 197, 0.1, False)])
@@ -95,8 +102,11 @@ def test_attention_core_rejects_unsupported_shapes():
     x = torch.randn(1, 300, 64, device=DEV)
     with pytest.raises(RuntimeError):
         A.attention_core(x, x, x, 1)
-    y = torch.randn(1, 8, 48, device=DEV)
+    y = torch.randn(1, 8, 40, device=DEV)
     with pytest.raises(RuntimeError):
-        A.attention_core(y, y, y, 2)
+        A.attention_core(y, y, y, 2)   # head_dim 20: not a multiple of 8
+    z = torch.randn(1, 8, 144, device=DEV)
+    with pytest.raises(RuntimeError):
+        A.attention_core(z, z, z, 2)   # head_dim 72 > 64
     with pytest.raises(RuntimeError):
         A.attention_core(torch.randn(1, 8, 64), torch.randn(1, 8, 64), torch.randn(1, 8, 64), 1)  # CPU tensors

@@ -57,11 +57,37 @@ def test_config1_classifier_training_steps_track_cpu_port():
     assert all(torch.equal(a, b) for a, b in zip(masks_r, masks_g))
 
 
-def test_config2_retrieval_forward_backward_vs_cpu_port():
-    """train_multimodal.py shape (image 160 -> 64 here to keep the CPU side short, embed 192, hidden 384,
-    batch 16): embeddings, loss and the gradients of every ternary layer, after the gradual-quantization
-    scheduler assigned per-layer sparsities."""
-    cfg = T.RetrievalCfg(name="t", vocab=500, embed_dim=192, hidden_dim=384, image_size=64, batch=16)
+def _anchored_misses(named_got, named_f32, named_f64, ref_mult, alpha_mult, skip=()):
+    """|gpu - f64| <= 1e-2 |f64| + 1e-3 max|f64| + ref_mult * max|cpu_fp32 - f64| per tensor (tests/test_gpu_dropin.py)."""
+    misses, checked, worst_ratio = [], 0, 0.0
+    for n, f64 in named_f64.items():
+        if f64 is None or any(n.endswith(s) for s in skip) or float(f64.abs().max()) < 1e-12:
+            continue
+        got, f32 = named_got[n].detach().cpu().double(), named_f32[n].double()
+        ref_err = float((f32 - f64).abs().max())
+        mult = alpha_mult if n.endswith(".alpha") else ref_mult
+        scale = float(f64.abs().max())
+        err = (got - f64).abs()
+        miss = err - (1e-2 * f64.abs() + 1e-3 * scale + mult * ref_err)
+        worst_ratio = max(worst_ratio, float((err - 1e-2 * f64.abs() - 1e-3 * scale).max()) / max(ref_err, 1e-30))
+        checked += 1
+        if float(miss.max()) > 0:
+            misses.append(f"{n}: over by {float(miss.max()):.3e} (|f64| max {scale:.3e}, cpu fp32 err {ref_err:.3e}, gpu err {float(err.max()):.3e})")
+    return misses, checked, worst_ratio
+
+
+@pytest.mark.parametrize("fused_attention", [False, True])
+def test_config2_retrieval_forward_backward_vs_cpu_port(fused_attention, monkeypatch):
+    """BASELINE config 2 at its real size (train_multimodal.py shape: image 160, embed 192, hidden 384, vocab 3000,
+    batch 16): the harness model on the B200 `atq` (fused FFN / gated residual / fused contrastive loss) against the
+    same model on the CPU oracle layers in float32 AND float64, after the gradual-quantization scheduler assigned
+    per-layer sparsities.  fused_attention=False keeps the reference's explicit matmul/softmax attention (torch fp32):
+    every gradient must be within tolerance + 2x the CPU fp32 path's own distance from float64 (measured: 1.9x).
+    fused_attention=True adds the tcgen05 attention core, whose operands are bf16 pairs (2^-17 per operand; head_dim 24
+    zero-padded to 64): the network is badly conditioned at init (saturated softmax, |dL/d embedding| ~ 6e2) and
+    amplifies that, so the bound is 16x the CPU fp32 path's own error (measured: 9.6x) -- an fp64-anchored statement."""
+    monkeypatch.setattr(M, "FUSED_ATTENTION_CORE", fused_attention)
+    cfg = T.FLICKR8K_SHAPE  # BASELINE config 2 at its real size (image 160, vocab 3000, batch 16)
     ref, _, man_r = T.build_retrieval(M.oracle_layers(), cfg, seed=42)
     mod, _, man_g = T.build_retrieval(atq, cfg, seed=42)
     mod.load_state_dict(ref.state_dict())
@@ -73,46 +99,33 @@ def test_config2_retrieval_forward_backward_vs_cpu_port():
     assert got == want and len(got) == 29
     ref.eval(); mod.eval()  # dropout off, BatchNorm uses running stats: deterministic on both sides
     images, captions, lengths = T.synthetic_batches(cfg, 1, seed=1)[0]
-    ri, rt = ref(images, captions, lengths)
+
+    def run_cpu(model, manager, dt):
+        model.zero_grad(set_to_none=True)
+        i, t = model(images.to(dt), captions, lengths)
+        loss = manager.compute_loss(i, t)
+        loss.backward()
+        return i.detach(), t.detach(), loss.detach(), {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in model.named_parameters()}
+
+    ri, rt, lr, g32 = run_cpu(ref, man_r, torch.float32)
+    ref.double()
+    di, dt_, ld, g64 = run_cpu(ref, man_r, torch.float64)
     gi, gt = mod(images.to(DEV), captions.to(DEV), lengths.to(DEV))
-    assert torch.allclose(gi.detach().cpu(), ri.detach(), rtol=1e-2, atol=2e-3)
-    assert torch.allclose(gt.detach().cpu(), rt.detach(), rtol=1e-2, atol=2e-3)
-    lr = man_r.compute_loss(ri, rt)
+    assert torch.allclose(gi.detach().cpu(), ri, rtol=1e-2, atol=1e-3)   # north_star tolerance on the embeddings
+    assert torch.allclose(gt.detach().cpu(), rt, rtol=1e-2, atol=1e-3)
     lg = man_g.compute_loss(gi, gt)
-    assert abs(float(lr.detach()) - float(lg.detach())) < 5e-3
-    lr.backward(); lg.backward()
-    # Gradients.  Close to the loss (projectors, pooling, last block) the CUDA path must match the fp32 port
-    # within 2 % of each tensor's max.  Further upstream the reference network is badly conditioned at
-    # init (saturated softmax attention: |dL/d embedding| ~ 2e3, and the CPU fp32 port itself only agrees
-    # with an fp64 run to 1e-2 there), so the bf16 hi+lo operands (2^-17 vs 2^-24) are amplified; those
-    # tensors are checked for direction (cosine) and magnitude instead.
-    gr = dict(ref.named_parameters())
-    near_loss = ("text_projector.", "text_norm.", "text_encoder.attention_pool.0", "text_encoder.attention_pool.2.weight",
-                 "text_encoder.attention_pool.2.alpha", "text_encoder.norm.", "text_encoder.layers.3.linear",
-                 "text_encoder.layers.3.self_attn.v_proj", "text_encoder.layers.3.self_attn.out_proj",
-                 "image_encoder.projector.weight", "image_encoder.projector.bias", "image_encoder.proj_norm.",
-                 "image_encoder.feature_norm.")
-    checked = strict = 0
-    for n, p in mod.named_parameters():
-        if p.grad is None:
-            assert gr[n].grad is None, n
-            continue
-        if n.endswith("k_proj.bias"):
-            continue  # softmax is invariant to a shift of all keys: this gradient is identically zero + rounding noise
-        a, b = p.grad.cpu().double().flatten(), gr[n].grad.double().flatten()
-        scale = float(b.abs().max())
-        if scale < 1e-8:
-            continue
-        err = float((a - b).abs().max()) / scale
-        if n.startswith(near_loss):
-            # alpha gradients are scalar sums of ~1e5 cancelling terms (the fp32 port is itself 1e-2 off fp64)
-            assert err <= (1e-1 if n.endswith(".alpha") else 2e-2), (n, err)
-            strict += 1
-        elif a.numel() > 1:
-            cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
-            assert cos >= 0.95 and err <= 0.6, (n, cos, err)
-        checked += 1
-    assert checked > 100 and strict >= 20
+    assert abs(float(lg.detach()) - float(ld)) <= 1e-3 + 2 * abs(float(lr) - float(ld))
+    lg.backward()
+    grads = {n: p.grad for n, p in mod.named_parameters()}
+    for n, g in g32.items():
+        assert (g is None) == (grads[n] is None), n
+    # k_proj.bias: softmax is invariant to a shift of all keys (identically zero + rounding noise); the fp32 ResNet
+    # trunk is torch / cuDNN code on the GPU side (its fp32 convolution algorithms differ from the CPU's by ~1e-3)
+    skip = ("k_proj.bias",) + tuple(n for n in g64 if n.startswith("image_encoder.base_model."))
+    mult = 16.0 if fused_attention else 2.0
+    misses, checked, worst = _anchored_misses(grads, g32, g64, mult, 4 * mult, skip)
+    assert checked > 100
+    assert not misses, f"worst (err - tol) / cpu-fp32-err ratio {worst:.1f}\n" + "\n".join(misses)
     # the batched re-quantization entry point: only image_projector (never executed on this path,
     # SURVEY 3.3) is still unquantized after a forward; a second call finds nothing stale
     assert atq.prepare_quantization(mod) == 1
