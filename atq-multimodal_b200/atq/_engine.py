@@ -53,6 +53,16 @@ def set_ste(enabled: bool) -> None:
     _STE = bool(enabled)
 
 
+def set_cta_pairs(enabled: bool) -> bool:
+    """GEMMs with a lo operand part run on CTA pairs (cta_group::2) by default; False forces single-CTA kernels.
+    Returns the previous setting."""
+    return bool(nv.lib.atq_set_cta_pairs(1 if enabled else 0))
+
+
+if os.environ.get("ATQ_CTA_PAIRS", "1") == "0":
+    nv.lib.atq_set_cta_pairs(0)
+
+
 def _use_lo() -> bool:
     return _MODE != "fast"
 
@@ -291,17 +301,16 @@ def split_scaled(x2: torch.Tensor, want_lo: bool = True):
 # last operand built on each stream is kept (with a strong reference to its source, so the memory cannot be recycled
 # under it) and reused while the source's (storage, version, layout, mode) still match.
 _LAST_SPLIT: dict = {}
-# (opt-in: under CUDA-graph capture of the whole step the reuse invalidates the capture -- cause not found -- and it
-#  saves two small launches per attention block, so it stays off by default)
-_SPLIT_REUSE = os.environ.get("ATQ_SPLIT_REUSE", "0") == "1"
+# (eager execution only: under CUDA-graph capture of the whole step the reuse invalidated the capture -- cause not
+#  found -- so lookups are skipped while the stream is capturing)
+_SPLIT_REUSE = os.environ.get("ATQ_SPLIT_REUSE", "1") == "1"
 _FUSED_SPLIT = os.environ.get("ATQ_FUSED_SPLIT", "1") == "1"
 
 
 def split_operand(x2: torch.Tensor, owner: Optional[torch.Tensor] = None):
     """The A operand of a GEMM in the current precision mode (see the module docstring)."""
-    if owner is not None and _SPLIT_REUSE:
-        capturing = torch.cuda.is_current_stream_capturing()
-        skey = (nv.device_index(x2), nv.stream_ptr(nv.device_index(x2)), capturing)
+    if owner is not None and _SPLIT_REUSE and not torch.cuda.is_current_stream_capturing():
+        skey = (nv.device_index(x2), nv.stream_ptr(nv.device_index(x2)))
         key = (x2.data_ptr(), owner._version, tuple(x2.shape), tuple(x2.stride()), _MODE)
         hit = _LAST_SPLIT.get(skey)
         if hit is not None and hit[0] == key and hit[1] is owner:
@@ -380,6 +389,19 @@ def tgemm(a, b, rows: int, cols: int, kdim: int, scale=None, bias=None, dot_ref=
             out.data_ptr(), cols, nv.ptr(dot_ref), 0 if dot_ref is None else dot_ref.stride(0), nv.ptr(dot_out),
             ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
     return out, dot_out
+
+
+def tgemm_absmax(a, b, rows: int, cols: int, kdim: int, bound_mul: float, scale=None, bias=None):
+    """tgemm whose epilogue also reduces max|out|: returns (out, slot) with slot the scale slot of `out` as a scaled
+    fp16 operand for bound = max|out| * bound_mul (no separate reduction pass over the output)."""
+    hi = a[0]
+    dev = nv.device_index(hi)
+    out = torch.empty((rows, cols), dtype=torch.float32, device=hi.device)
+    slot = nv.new_slot(hi.device)
+    oa, ob = nv.operand(*a), nv.operand(*b)
+    nv.call("atq_tgemm_absmax", dev, rows, cols, kdim, ctypes.byref(oa), ctypes.byref(ob), nv.ptr(scale), nv.ptr(bias),
+            out.data_ptr(), cols, slot.data_ptr(), float(bound_mul), nv.stream_ptr(dev))
+    return out, slot
 
 
 def tgemm_packed(a, packed_b: torch.Tensor, rows: int, cols: int, kdim: int, scale=None, bias=None, dot_ref=None):
@@ -722,9 +744,12 @@ class _RPBFFNFn(torch.autograd.Function):
         N = x2.shape[0]
         lo, f16 = _use_lo(), _use_f16()
         xa = split_operand(x2, x)
-        y1, _ = tgemm(xa, ops1.w, N, H, K, bias=None if b1 is None else b1.detach())
-        # |dropout(gelu(y))| <= max|y| / (1-p): the hidden operand's scale comes from one reduction over y1
-        da = gelu_dropout_split(y1, p, seed, lo, absmax_slot(y1, _keep_bound(p)) if f16 else None)
+        # |dropout(gelu(y))| <= max|y| / (1-p): the hidden operand's scale comes from max|y1|, reduced in the GEMM epilogue
+        if f16:
+            y1, slot_d = tgemm_absmax(xa, ops1.w, N, H, K, _keep_bound(p), bias=None if b1 is None else b1.detach())
+        else:
+            (y1, _), slot_d = tgemm(xa, ops1.w, N, H, K, bias=None if b1 is None else b1.detach()), None
+        da = gelu_dropout_split(y1, p, seed, lo, slot_d)
         y2, _ = tgemm(da, ops2.w, N, M, H, bias=None if b2 is None else b2.detach())
         tensors = [y1, mask1, mask2, xa[0], da[0]] + ([xa[1], da[1]] if lo else [])
         ctx.save_for_backward(*tensors)
@@ -752,11 +777,14 @@ class _RPBFFNFn(torch.autograd.Function):
             ga2, db2 = split_operand_colsum(g2, lo, f16)
         else:
             ga2, db2 = (split_scaled(g2, lo) if f16 else split_bf16(g2, lo)), None
-        dd, _ = tgemm(ga2, w2_t, N, H, M)  # gradient w.r.t. the dropped activations, fp32 [N, H]
+        # gradient w.r.t. the dropped activations, fp32 [N, H]; |dd * keep/(1-p) * gelu'(y)| <= max|dd| * 1.13 / (1-p)
+        if f16:
+            dd, slot_g = tgemm_absmax(ga2, w2_t, N, H, M, 1.13 * _keep_bound(p))
+        else:
+            (dd, _), slot_g = tgemm(ga2, w2_t, N, H, M), None
         mk2 = mask2 if mask2.is_contiguous() else mask2.contiguous()
         dw2, dalpha2 = tgemm_dw_masked(mn_view(ga2), mn_view(da), M, H, N, mask=mk2, packed=packed2)
-        # |dd * keep/(1-p) * gelu'(y)| <= max|dd| * 1.13 / (1-p)
-        g1a, db1 = gelu_dropout_bwd_split_colsum(dd, y1, p, ctx.seed, lo, absmax_slot(dd, 1.13 * _keep_bound(p)) if f16 else None)
+        g1a, db1 = gelu_dropout_bwd_split_colsum(dd, y1, p, ctx.seed, lo, slot_g)
         dx = None
         if ctx.needs_input_grad[0]:
             dx, _ = tgemm(g1a, w1_t, N, K, H)

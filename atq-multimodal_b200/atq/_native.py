@@ -68,9 +68,12 @@ _SIGS = {
     "atq_build_ternary_operands": (c_int, [c_int, _P, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int, _P]),
     "atq_build_mixed_operands": (c_int, [c_int, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P,
                                          c_int64, _P, _P]),
+    "atq_set_cta_pairs": (c_int, [c_int]),
     "atq_workspace_bytes_tgemm": (c_size_t, [c_int64, c_int64]),
     "atq_tgemm": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P, _P,
                           c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
+    "atq_tgemm_absmax": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P, _P,
+                                 c_int64, _P, c_float, _P]),
     "atq_tgemm_packed": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), _P, _P, _P, _P,
                                  c_int64, _P, c_int64, _P, _P, c_size_t, _P]),
     "atq_tgemm_fwd": (c_int, [c_int, c_int64, c_int64, c_int64, POINTER(BF16Operand), POINTER(BF16Operand), _P, _P,

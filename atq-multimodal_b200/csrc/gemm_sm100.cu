@@ -91,6 +91,7 @@ __device__ __forceinline__ void unpack16_to_bf16(uint32_t w, uint4& lo8, uint4& 
 // kernel
 // ------------------------------------------------------------------------------------------
 enum { EPI_LINEAR = 0, EPI_MASKED = 1 };
+static bool g_cta_pairs = true;  // atq_set_cta_pairs(): A/B switch for the cta_group::2 kernels
 
 struct GemmParams {
   int64_t rows, cols, kdim;
@@ -110,14 +111,16 @@ struct GemmParams {
   const float* inv_a;       // nullable device scalars: 1/scale of a scaled-fp16 operand (exact powers of two);
   const float* inv_b;       //   the accumulator is multiplied by both before anything else in the epilogue
   int f16;                  // operands are fp16 (both), else bf16
+  unsigned int* absmax_bits;  // nullable (LINEAR): atomicMax of the bit pattern of max|out| (slot[0] of a scale slot)
 };
 
 constexpr int kStagingBytes = 4 * 32 * 36 * 4;  // per-epilogue-warp [32][36] fp32 transposition buffers (rows 16-byte aligned)
 
-template <int NUM_A, int NUM_B, int BLOCK_N, int BK = BLOCK_K>
+template <int NUM_A, int NUM_B, int BLOCK_N, int BK = BLOCK_K, bool CTA2 = false>
 struct GemmCfg {
   static constexpr int kABytes = BLOCK_M * BK * 2;
-  static constexpr int kBBytes = BLOCK_N * BK * 2;
+  static constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;  // a CTA of a pair holds half of the B tile
+  static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = NUM_A * kABytes + NUM_B * kBBytes;
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -133,12 +136,23 @@ struct GemmCfg {
 // (column tile fastest, so the CTAs working at the same time share A tiles through L2 and the
 // whole B operand stays L2-resident).  The accumulator is double-buffered in TMEM: the MMA warp
 // starts tile i+1 while the epilogue warps drain tile i.
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK, int BK = BLOCK_K>
+//
+// CTA2 = true: the same kernel run by CTA PAIRS (cluster of 2, launched with a cluster dimension): a pair owns a
+// 256 x BLOCK_N tile, each CTA loads its 128 rows of A and HALF of the B tile, the leader issues
+// tcgen05.mma.cta_group::2 (M = 256), every CTA drains its own 128 accumulator rows.  B shared-memory reads per
+// flop halve, which is what the 128-wide dual-accumulator tiles (hi/lo operands) are short of.
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK, int BK = BLOCK_K, bool CTA2 = false>
 __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     tgemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const GemmParams p) {
-  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N, BK>;
+  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N, BK, CTA2>;
+  static_assert(!(CTA2 && (B_PACKED || BK != 64 || BLOCK_N != 128)), "CTA pairs: 128-wide TMA-fed tiles only");
+  constexpr int kPairM = CTA2 ? 2 * BLOCK_M : BLOCK_M;  // rows of the tile a work item covers
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0u;
+  const int work_first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int work_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int kStages = Cfg::kStages;
   constexpr bool A_MN = (LAYOUT == LAYOUT_MM), B_MN = (LAYOUT != LAYOUT_KK);
   static_assert(!(B_PACKED && LAYOUT != LAYOUT_KK), "packed B is K-major");
@@ -165,7 +179,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
   const int lane = threadIdx.x & 31;
   const int num_kb = (int)((p.kdim + BK - 1) / BK);
   const int tiles_n = (int)((p.cols + BLOCK_N - 1) / BLOCK_N);
-  const int tiles_m = (int)((p.rows + BLOCK_M - 1) / BLOCK_M);
+  const int tiles_m = (int)((p.rows + kPairM - 1) / kPairM);
   const int num_tiles = tiles_n * tiles_m;
   const int splits = p.splits > 1 ? p.splits : 1;
   const int num_work = num_tiles * splits;
@@ -184,15 +198,17 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tmem_full_bar(a), 1);
-      mbar_init(tmem_empty_bar(a), 4);  // one arrival per epilogue warp
+      mbar_init(tmem_empty_bar(a), CTA2 ? 8 : 4);  // one arrival per epilogue warp (of both CTAs of a pair: the leader's copy counts)
     }
     fence_barrier_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if constexpr (CTA2) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+    else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // both CTAs' barriers initialised and TMEM allocated before any cross-CTA signal
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -201,14 +217,19 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      // (CTA pairs: the loads of both CTAs count on the leader's full barrier)
+      auto tma_load_2d = [&](uint32_t dst, const CUtensorMap* map, int32_t c0, int32_t c1, uint32_t bar) {
+        if constexpr (CTA2) atq::tma_load_2d_2sm(dst, map, c0, c1, bar);
+        else atq::tma_load_2d(dst, map, c0, c1, bar);
+      };
+      for (int w = work_first; w < num_work; w += work_step) {
         const int t = w % num_tiles;
-        const int32_t n0 = (t % tiles_n) * BLOCK_N;
-        const int32_t m0 = (t / tiles_n) * BLOCK_M;
+        const int32_t n0 = (t % tiles_n) * BLOCK_N + (int32_t)cta_rank * Cfg::kBRows;       // this CTA's part of the B tile
+        const int32_t m0 = (t / tiles_n) * kPairM + (int32_t)cta_rank * BLOCK_M;            // this CTA's rows of A
         for (int kb = kb_lo(w); kb < kb_hi(w); ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(stage), B_PACKED ? NUM_A * Cfg::kABytes : Cfg::kStageBytes);
+          if (leader) mbar_expect_tx(full_bar(stage), (B_PACKED ? NUM_A * Cfg::kABytes : Cfg::kStageBytes) * (CTA2 ? 2 : 1));
           const int32_t kc = kb * BK;
           if constexpr (!A_MN) {
             tma_load_2d(sa, &map_a_hi, kc, m0, full_bar(stage));
@@ -227,7 +248,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
               if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes, &map_b_lo, kc, n0, full_bar(stage));
             } else {
 #pragma unroll
-              for (int j = 0; j < (BLOCK_N + 63) / 64; ++j) {
+              for (int j = 0; j < (Cfg::kBRows + 63) / 64; ++j) {
                 tma_load_2d(sb + j * kMnBlock, &map_b_hi, n0 + 64 * j, kc, full_bar(stage));
                 if (NUM_B == 2) tma_load_2d(sb + Cfg::kBBytes + j * kMnBlock, &map_b_lo, n0 + 64 * j, kc, full_bar(stage));
               }
@@ -238,14 +259,23 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       }
     }
   } else if (warp_idx == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (the leader CTA of a pair) =================
+    if (lane == 0 && leader) {
+      auto umma_bf16 = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if constexpr (CTA2) atq::umma_bf16_2sm(d, da, db, id, acc);
+        else atq::umma_bf16(d, da, db, id, acc);
+      };
+      auto umma_commit = [&](uint32_t bar) {
+        if constexpr (CTA2) atq::umma_commit_2sm(bar);
+        else atq::umma_commit(bar);
+      };
       // a/b format fields (bits 7-9, 10-12): 1 = bf16, 0 = fp16
-      const uint32_t idesc = p.f16 ? (make_idesc<BLOCK_N, A_MN, B_MN>() & ~((7u << 7) | (7u << 10))) : make_idesc<BLOCK_N, A_MN, B_MN>();
+      uint32_t idesc = p.f16 ? (make_idesc<BLOCK_N, A_MN, B_MN>() & ~((7u << 7) | (7u << 10))) : make_idesc<BLOCK_N, A_MN, B_MN>();
+      if constexpr (CTA2) idesc = (idesc & ~(31u << 24)) | ((uint32_t)(kPairM >> 4) << 24);  // M = 256
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+      for (int w = work_first; w < num_work; w += work_step, ++it) {
         const int a = it & 1;
         const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
         mbar_wait(tmem_empty_bar(a), aphase ^ 1u);  // epilogue has drained this accumulator buffer
@@ -358,6 +388,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
     // 1/(s_a s_b) of scaled-fp16 operands: exact power of two, applied to the raw accumulator first
     const float opscale = (p.inv_a != nullptr ? __ldg(p.inv_a) : 1.f) * (p.inv_b != nullptr ? __ldg(p.inv_b) : 1.f);
     float partial = 0.f;
+    float amax = 0.f;  // max |stored output| of this thread (p.absmax_bits: the consumer's operand scale, no extra pass)
     // 128-bit path: every lane owns 4 consecutive columns of 8 rows per chunk (4x fewer shared/global
     // instructions than lane = column); needs 16-byte aligned rows on every tensor the epilogue touches
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; };
@@ -367,12 +398,17 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
                                            : (p.mask == nullptr || al16(p.mask)));
     const int vq = lane & 7, vrg = lane >> 3;
     int it = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+    // the MMA issuer waits on the LEADER's tmem_empty barrier: both CTAs of a pair arrive there
+    auto release_acc = [&](int a) {
+      if constexpr (CTA2) mbar_arrive_leader(tmem_empty_bar(a));
+      else mbar_arrive(tmem_empty_bar(a));
+    };
+    for (int w = work_first; w < num_work; w += work_step, ++it) {
       const int a = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       const int t = w % num_tiles;
       const int64_t n0 = (int64_t)(t % tiles_n) * BLOCK_N;
-      const int64_t m0 = (int64_t)(t / tiles_n) * BLOCK_M;
+      const int64_t m0 = (int64_t)(t / tiles_n) * kPairM + (int64_t)cta_rank * BLOCK_M;  // this CTA's accumulator rows
       float* const out = p.out + (int64_t)(w / num_tiles) * p.split_stride;  // split-K partial slab
       const int64_t r_base = m0 + quarter * 32;
       // number of 32-column chunks of this tile that hold real output (warp-uniform)
@@ -411,7 +447,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
         tcgen05_fence_after();
         if (nch == 0) {
           tcgen05_fence_before();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+          if (lane == 0) release_acc(a);
         }
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {
@@ -429,7 +465,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
           }
           if (ch == nch - 1) {  // everything this warp needs has left TMEM: hand the buffer back
             tcgen05_fence_before();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+            if (lane == 0) release_acc(a);
           }
           // thread = accumulator row: 8 x 16-byte stores, 144-byte row pitch (conflict-free per quarter-warp)
 #pragma unroll
@@ -452,6 +488,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
               if constexpr (EPI == EPI_LINEAR) {
                 if (p.dot_ref != nullptr) partial += (v.x * vf[g].x + v.y * vf[g].y) + (v.z * vf[g].z + v.w * vf[g].w);
                 o = make_float4(v.x * scale + bias4.x, v.y * scale + bias4.y, v.z * scale + bias4.z, v.w * scale + bias4.w);
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
               } else {
                 const uint32_t b = vc[g];
                 const float t0 = (float)(b & 3u) - 1.f, t1 = (float)((b >> 2) & 3u) - 1.f;
@@ -479,7 +516,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       tcgen05_fence_after();
       if (nch == 0) {
         tcgen05_fence_before();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+        if (lane == 0) release_acc(a);
       }
 #pragma unroll 1
       for (int ch = 0; ch < nch; ++ch) {
@@ -494,7 +531,7 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
         }
         if (ch == nch - 1) {
           tcgen05_fence_before();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(a));
+          if (lane == 0) release_acc(a);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) stg[lane * 36 + j] = __uint_as_float(acc[j]);  // 4-way bank conflict accepted here
@@ -507,7 +544,9 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
             const float v = stg[rr * 36 + lane] * opscale;
             if constexpr (EPI == EPI_LINEAR) {
               if (p.dot_ref != nullptr) partial += v * __ldg(p.dot_ref + (r_base + rr) * p.dot_ref_pitch + c);
-              out[(r_base + rr) * p.out_pitch + c] = v * scale + bias;
+              const float o1 = v * scale + bias;
+              amax = fmaxf(amax, fabsf(o1));
+              out[(r_base + rr) * p.out_pitch + c] = o1;
             } else {
               const int64_t i = (r_base + rr) * p.cols + c;  // mask / codec bytes are contiguous [rows, cols]
               const float mk = p.mask != nullptr ? __ldg(p.mask + i) : 1.f;
@@ -524,16 +563,35 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       partial = warp_sum(partial);
       if (lane == 0) s_part[quarter] = partial;
     }
+    if (EPI == EPI_LINEAR && p.absmax_bits != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      if (lane == 0) atomicMax(p.absmax_bits, __float_as_uint(amax));  // non-negative floats order as uints
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer may still be reading / signalling: nobody leaves early
+  else __syncthreads();
   if (warp_idx == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if constexpr (CTA2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
   if (p.partials != nullptr && threadIdx.x == 0) {
     p.partials[blockIdx.x] = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
   }
+}
+
+// scale slot written by a GEMM epilogue (slot[0] = bits of max|out|): derive {scale, 1/scale} for bound = max * bound_mul
+// and re-arm the slot (CUDA-graph replays)
+__global__ void slot_finalize_kernel(float* slot, float bound_mul) {
+  unsigned int* bits = reinterpret_cast<unsigned int*>(slot);
+  const float b = __uint_as_float(bits[0]) * bound_mul;
+  float sc, inv;
+  pow2_scale_for(b, sc, inv);
+  slot[1] = sc;
+  slot[2] = inv;
+  bits[0] = 0u;
 }
 
 // deterministic final sum of the per-CTA partials
@@ -644,9 +702,9 @@ static int make_map_mn(CUtensorMap* map, const uint16_t* ptr, int64_t mn, int64_
   return ATQ_OK;
 }
 
-template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK, int BK = BLOCK_K>
+template <int NUM_A, int NUM_B, int BLOCK_N, int EPI, bool B_PACKED = false, int LAYOUT = LAYOUT_KK, int BK = BLOCK_K, bool CTA2 = false>
 static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, const GemmParams& p, cudaStream_t stream, int* grid_used) {
-  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N, BK>;
+  using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N, BK, CTA2>;
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   int r;
   constexpr bool A_MN = (LAYOUT == LAYOUT_MM), B_MN = (LAYOUT != LAYOUT_KK);
@@ -654,7 +712,7 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
     return A_MN ? make_map_mn(m, ptr, p.rows, p.kdim, a->pitch, BK) : make_map(m, ptr, p.rows, p.kdim, a->pitch, BLOCK_M, BK);
   };
   auto map_b = [&](CUtensorMap* m, const uint16_t* ptr) {
-    return B_MN ? make_map_mn(m, ptr, p.cols, p.kdim, b->pitch, BK) : make_map(m, ptr, p.cols, p.kdim, b->pitch, BLOCK_N, BK);
+    return B_MN ? make_map_mn(m, ptr, p.cols, p.kdim, b->pitch, BK) : make_map(m, ptr, p.cols, p.kdim, b->pitch, Cfg::kBRows, BK);
   };
   if ((r = map_a(&ma_hi, a->hi)) != ATQ_OK) return r;
   if constexpr (!B_PACKED) {
@@ -670,7 +728,7 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
   pp.f16 = a->format != 0;
   pp.inv_a = a->inv_scale;
   pp.inv_b = B_PACKED ? nullptr : b->inv_scale;
-  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED, LAYOUT, BK>;
+  auto kern = tgemm_kernel<NUM_A, NUM_B, BLOCK_N, EPI, B_PACKED, LAYOUT, BK, CTA2>;
   static bool attr_done_dev[64] = {false};  // per instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -683,17 +741,43 @@ static int launch_cfg(const atq_bf16_operand* a, const atq_bf16_operand* b, cons
     }
     attr_done = true;
   }
-  const int64_t tiles = ((p.cols + BLOCK_N - 1) / BLOCK_N) * ((p.rows + BLOCK_M - 1) / BLOCK_M);
+  constexpr int kTileM = CTA2 ? 2 * BLOCK_M : BLOCK_M;
+  const int64_t tiles = ((p.cols + BLOCK_N - 1) / BLOCK_N) * ((p.rows + kTileM - 1) / kTileM);
   if (tiles > 0x7fffffff) {
     set_error("tgemm: too many tiles (%lld)", (long long)tiles);
     return ATQ_EINVAL;
   }
   const int sms = sm_count(dev);
   const int64_t work = tiles * (p.splits > 1 ? p.splits : 1);
-  const int grid = (int)(work < sms ? work : sms);
+  int grid = (int)(work < sms ? work : sms);
+  cudaError_t e;
+  if constexpr (CTA2) {
+    // one cluster of 2 CTAs (the two SMs of a TPC) per work item; persistent over min(work, SMs / 2) pairs
+    const int pairs = (int)(work < sms / 2 ? work : sms / 2);
+    grid = 2 * pairs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)gemm_threads(B_PACKED, BLOCK_N));
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, ma_hi, ma_lo, mb_hi, mb_lo, pp);
+    if (e != cudaSuccess) {
+      set_error("tgemm (CTA pair) launch failed: %s", cudaGetErrorString(e));
+      return ATQ_ECUDA;
+    }
+  } else {
+    kern<<<grid, gemm_threads(B_PACKED, BLOCK_N), Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pp);
+  }
   *grid_used = grid;
-  kern<<<grid, gemm_threads(B_PACKED, BLOCK_N), Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pp);
-  cudaError_t e = cudaGetLastError();
+  e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("tgemm launch failed: %s", cudaGetErrorString(e));
     return ATQ_ECUDA;
@@ -717,6 +801,16 @@ static int dispatch_layout(const atq_bf16_operand* a, const atq_bf16_operand* b,
   }
   // operands with a lo part keep two accumulators per tile (hi x hi, corrections): 4 x BLOCK_N TMEM columns
   // double-buffered, so those kernels use 128-wide tiles; single-term GEMMs use 256-wide tiles when wide enough
+  // CTA pairs (cta_group::2) once the output has at least one 256-row tile per pair-column: halves the B-operand
+  // shared-memory reads per flop of the 128-wide dual-accumulator tiles
+  const bool pairs = g_cta_pairs && p.rows >= 256 && p.cols >= 128;
+#define ATQ_GO2(NA, NB) return launch_cfg<NA, NB, 128, EPI, false, LAYOUT, BLOCK_K, true>(a, b, p, stream, grid_used)
+  if (pairs) {
+    if (a2 && b2) ATQ_GO2(2, 2);
+    if (b2) ATQ_GO2(1, 2);
+    if (a2) ATQ_GO2(2, 1);
+  }
+#undef ATQ_GO2
   if (a2 && b2) ATQ_GO(2, 2, 128);
   if (b2) ATQ_GO(1, 2, 128);
   if (a2) ATQ_GO(2, 1, 128);
@@ -761,8 +855,40 @@ using namespace atq;
 
 extern "C" {
 
+int atq_set_cta_pairs(int enabled) {
+  const int old = g_cta_pairs ? 1 : 0;
+  g_cta_pairs = enabled != 0;
+  return old;
+}
+
 size_t atq_workspace_bytes_tgemm(int64_t rows, int64_t cols) {
   return (size_t)(((num_tiles_upper(rows, cols) * sizeof(float)) + 255) & ~(size_t)255);
+}
+
+int atq_tgemm_absmax(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf16_operand* a, const atq_bf16_operand* b,
+                     const float* scale, const float* bias, float* out, int64_t out_pitch, float* out_scale_slot, float bound_mul,
+                     atq_stream_t stream_) {
+  ATQ_CHECK_ARG(rows > 0 && cols > 0 && kdim > 0 && out != nullptr && out_pitch >= cols, "bad shape or null output");
+  ATQ_CHECK_ARG(out_scale_slot != nullptr && bound_mul > 0.f, "needs a scale slot and a positive bound_mul");
+  int r;
+  if ((r = check_operand(a, "a")) != ATQ_OK) return r;
+  if ((r = check_operand(b, "b")) != ATQ_OK) return r;
+  ATQ_CHECK_ARG(a->pitch >= (a->mn_major ? rows : kdim) && b->pitch >= (b->mn_major ? cols : kdim),
+                "operand pitch smaller than its contiguous extent");
+  ATQ_CHECK_ARG(a->format == b->format, "A and B operands must have the same element format (tcgen05 kind::f16)");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.rows = rows; p.cols = cols; p.kdim = kdim;
+  p.out = out; p.out_pitch = out_pitch;
+  p.scale = scale; p.bias = bias;
+  p.absmax_bits = reinterpret_cast<unsigned int*>(out_scale_slot);
+  int grid = 0;
+  if ((r = dispatch<EPI_LINEAR>(a, b, p, stream, &grid)) != ATQ_OK) return r;
+  slot_finalize_kernel<<<1, 1, 0, stream>>>(out_scale_slot, bound_mul);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
 }
 
 int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim, const atq_bf16_operand* a, const atq_bf16_operand* b,

@@ -196,6 +196,9 @@ typedef struct {
  * K8 dX:  dX[N,K] = scale * (dY[N,M] . Bt[K,M]^T); with dot_ref = X it also returns
  *  dot_out = sum(acc .* X) = d(alpha) of TernaryLinear (autograd's sum(G.*T)).
  * Both are this one entry point: D[rows,cols] = scale*(A . B^T) (+bias[cols]).           */
+/* GEMMs with a lo operand part run on CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) when rows >= 256 and
+ * cols >= 128; atq_set_cta_pairs(0) forces the single-CTA kernels (A/B measurements).  Returns the previous setting. */
+int atq_set_cta_pairs(int enabled);
 size_t atq_workspace_bytes_tgemm(int64_t rows, int64_t cols);
 int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim,
               const atq_bf16_operand* a, const atq_bf16_operand* b,
@@ -203,6 +206,13 @@ int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim,
               float* out, int64_t out_pitch,
               const float* dot_ref, int64_t dot_ref_pitch, float* dot_out,
               void* ws, size_t ws_bytes, atq_stream_t stream);
+/* atq_tgemm (scale, bias epilogue) that also produces the scale slot of ITS OUTPUT as a scaled-fp16 operand:
+ * the epilogue folds max|out| into out_scale_slot[0] (zero on entry), a one-thread kernel then writes
+ * slot[1..2] = {s, 1/s} for bound = max|out| * bound_mul and re-arms slot[0].  Saves the reduction pass over the
+ * output when the consumer is an operand split (the FFN activation between linear1 and linear2). */
+int atq_tgemm_absmax(int device, int64_t rows, int64_t cols, int64_t kdim,
+                     const atq_bf16_operand* a, const atq_bf16_operand* b, const float* scale, const float* bias,
+                     float* out, int64_t out_pitch, float* out_scale_slot, float bound_mul, atq_stream_t stream);
 /* Same contraction with B given as the 2-bit codec bytes of T ([cols, kdim/4] row-major, i.e. the
  * public packed format of a [cols, kdim] ternary matrix; kdim % 64 == 0, 16-byte aligned).
  * Converter warps expand each 16-byte codec row segment to a 128-byte bf16 row of the

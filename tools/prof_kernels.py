@@ -42,5 +42,25 @@ if which in ("all", "gemm"):
                     xi = x.clone().requires_grad_(True)
                     y = mod(xi)
                     y.backward(gy)
+if which in ("all", "codec"):
+    # whole-model codec kernels (16 layers of 4096 x 4096 = 268 M weights), absmax / split of the scaled-fp16 format
+    ws = [(torch.rand(4096, 4096, device=dev, generator=g) * 2 - 1) / 64 for _ in range(16)]
+    ss = [0.1 + 0.01 * i for i in range(16)]
+    for _ in range(reps):
+        thr = eng.adaptive_threshold_batched(ws, ss)
+        packed = eng.ternarize_pack2_batched(ws, thr)
+        outs, _ = eng.unpack2_batched(packed, [t.numel() for t in ws])
+        repacked, _ = eng.pack2_from_f32_batched(outs)
+        op = eng.split_operand(x)                                   # absmax_scale_kernel + split_flat_kernel (fp16 pair)
+        small = eng.split_operand(x[:800, :192].contiguous())       # split_scaled_cluster_kernel
+        del outs, repacked
+if which in ("all", "loss"):
+    from atq.contrastive import HardNegativeMiningInfoNCE
+    crit = HardNegativeMiningInfoNCE()
+    img = torch.randn(4096, 768, device=dev, generator=g, requires_grad=True)
+    txt = (0.5 * img.detach() + torch.randn(4096, 768, device=dev, generator=g)).requires_grad_(True)
+    for _ in range(reps):
+        img.grad = txt.grad = None
+        crit(img, txt).backward()
 torch.cuda.synchronize()
 print("done")
