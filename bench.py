@@ -419,7 +419,7 @@ class CallProfiler:
     """Brackets every C-ABI call with CUDA events (a separate, untimed pass of the same step)."""
 
     FLOPS = {"atq_tgemm": lambda a: 2.0 * a[0] * a[1] * a[2], "atq_tgemm_dw_masked": lambda a: 2.0 * a[0] * a[1] * a[2],
-             "atq_tgemm_packed": lambda a: 2.0 * a[0] * a[1] * a[2]}
+             "atq_tgemm_packed": lambda a: 2.0 * a[0] * a[1] * a[2], "atq_tgemm_absmax": lambda a: 2.0 * a[0] * a[1] * a[2]}
 
     def __init__(self):
         self.records = []
@@ -562,7 +562,7 @@ def measure_workload(args, cfg, steps, warmup, ctx, use_graph, clock_sampler=Non
     # atq_tgemm_dw_masked): its calls are aggregated; a non-GEMM kernel is only named if no GEMM ran
     gemm_calls = sum(d["calls"] for n, d in summ.items() if d["flops"] > 0)
     if gemm_ms > 0:
-        top = ("tgemm_kernel (atq_tgemm + atq_tgemm_dw_masked + atq_tgemm_packed)", {"ms": gemm_ms * 2, "flops": gemm_fl * 2, "calls": gemm_calls})
+        top = ("tgemm_kernel (atq_tgemm + atq_tgemm_absmax + atq_tgemm_dw_masked + atq_tgemm_packed)", {"ms": gemm_ms * 2, "flops": gemm_fl * 2, "calls": gemm_calls})
     else:
         top = max(summ.items(), key=lambda kv: kv[1]["ms"]) if summ else None
     if top is not None:
