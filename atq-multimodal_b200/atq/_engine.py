@@ -301,8 +301,7 @@ def split_scaled(x2: torch.Tensor, want_lo: bool = True):
 # last operand built on each stream is kept (with a strong reference to its source, so the memory cannot be recycled
 # under it) and reused while the source's (storage, version, layout, mode) still match.
 _LAST_SPLIT: dict = {}
-# (eager execution only: under CUDA-graph capture of the whole step the reuse invalidated the capture -- cause not
-#  found -- so lookups are skipped while the stream is capturing)
+# (skipped while the stream is capturing: a captured step re-runs the kernels anyway and the saving is two small launches)
 _SPLIT_REUSE = os.environ.get("ATQ_SPLIT_REUSE", "1") == "1"
 _FUSED_SPLIT = os.environ.get("ATQ_FUSED_SPLIT", "1") == "1"
 
@@ -313,10 +312,13 @@ def split_operand(x2: torch.Tensor, owner: Optional[torch.Tensor] = None):
         skey = (nv.device_index(x2), nv.stream_ptr(nv.device_index(x2)))
         key = (x2.data_ptr(), owner._version, tuple(x2.shape), tuple(x2.stride()), _MODE)
         hit = _LAST_SPLIT.get(skey)
-        if hit is not None and hit[0] == key and hit[1] is owner:
+        if hit is not None and hit[0] == key:
             return hit[2]
         op = split_operand(x2)
-        _LAST_SPLIT[skey] = (key, owner, op, x2)
+        # pin the source MEMORY (so the key cannot match a recycled allocation) through a detached alias: holding the
+        # tensor itself would keep its autograd graph -- and the AccumulateGrad nodes of every upstream parameter, bound
+        # to whatever stream that step ran on -- alive into the next step (this is what broke whole-step graph capture)
+        _LAST_SPLIT[skey] = (key, x2.detach(), op)
         return op
     if _use_f16():
         return split_scaled(x2)
