@@ -59,8 +59,8 @@ def set_cta_pairs(enabled: bool) -> bool:
     return bool(nv.lib.atq_set_cta_pairs(1 if enabled else 0))
 
 
-if os.environ.get("ATQ_CTA_PAIRS", "1") == "0":
-    nv.lib.atq_set_cta_pairs(0)
+if os.environ.get("ATQ_CTA_PAIRS", "1") != "1":
+    nv.lib.atq_set_cta_pairs(int(os.environ["ATQ_CTA_PAIRS"]))  # 0 = single CTA, 5 = pairs without the 256-wide tiles
 
 
 def _use_lo() -> bool:
@@ -443,9 +443,11 @@ def tgemm_dw_masked(dy_t, x_t, m_out: int, k_in: int, n_tok: int, mask=None, pac
 # ---------------------------------------------------------------------------------------
 
 class LayerOperands:
-    __slots__ = ("key", "thr", "packed", "packed_t", "w", "w_t")
+    __slots__ = ("key", "thr", "packed", "packed_t", "w", "w_t", "saw_grad", "hook_param")
 
     def __init__(self):
+        self.saw_grad = False    # a gradient has reached the weight at least once (TernaryLinear: normally never)
+        self.hook_param = None   # the Parameter object the gradient hook is registered on
         self.key = None
         self.thr = None
         self.packed = None    # 2-bit codec bytes of T, public layout [M*K/4]
@@ -478,8 +480,10 @@ def notify_weights_changed() -> None:
     _OPT_STEPS += 1
 
 
-def _key(weight, alpha, mask, sparsity_target, threshold_factor):
-    return (_OPT_STEPS, weight.data_ptr(), weight._version, tuple(weight.shape),
+def _key(weight, alpha, mask, sparsity_target, threshold_factor, frozen=False):
+    # frozen: a TernaryLinear weight that has never received a gradient (grad None => every optimizer skips
+    # it, weight decay included) cannot be changed by an optimizer step, so the step counter is left out of its key
+    return (0 if frozen else _OPT_STEPS, weight.data_ptr(), weight._version, tuple(weight.shape),
             None if alpha is None else (alpha.data_ptr(), alpha._version),
             None if mask is None else (mask.data_ptr(), mask._version),
             float(sparsity_target), float(threshold_factor), _MODE)
@@ -490,7 +494,15 @@ def layer_operands(cache: LayerOperands, weight, alpha, mask, sparsity_target, t
                    thr: Optional[torch.Tensor] = None, slot: Optional[torch.Tensor] = None) -> LayerOperands:
     """mask None -> TernaryLinear operands (T exact in bf16; alpha applied in the GEMM epilogue).
     mask given -> RPB mixed weight Wm = T*alpha*(1-mask) + W*mask as bf16 hi/lo."""
-    key = _key(weight, alpha if mask is not None else None, mask, sparsity_target, threshold_factor)
+    frozen = False
+    if mask is None and isinstance(weight, torch.nn.Parameter):
+        if cache.hook_param is not weight:  # (re-)arm the detector on this Parameter object
+            cache.hook_param, cache.saw_grad = weight, False
+            if weight.requires_grad:
+                # (autograd calls the hook with None when the only consumer returns no gradient: that does not count)
+                weight.register_hook(lambda g, c=cache: setattr(c, "saw_grad", True) if g is not None else None)
+        frozen = not cache.saw_grad and not _STE
+    key = _key(weight, alpha if mask is not None else None, mask, sparsity_target, threshold_factor, frozen)
     if cache.key == key:
         return cache
     w = nv.require_f32(weight.detach(), "weight")
@@ -555,7 +567,8 @@ def prepare_quantization(model, threshold_factor=0.05) -> int:
         mask = getattr(m, "precision_mask", None)
         s = getattr(m, "sparsity_target", 0.3)
         alpha = m.alpha if mask is not None else None
-        if cache.key != _key(m.weight, alpha, mask, s, threshold_factor):
+        frozen = mask is None and cache.hook_param is m.weight and not cache.saw_grad and not _STE
+        if cache.key != _key(m.weight, alpha, mask, s, threshold_factor, frozen):
             stale.append((m, cache, alpha, mask, s))
     if not stale:
         return 0

@@ -91,7 +91,8 @@ __device__ __forceinline__ void unpack16_to_bf16(uint32_t w, uint4& lo8, uint4& 
 // kernel
 // ------------------------------------------------------------------------------------------
 enum { EPI_LINEAR = 0, EPI_MASKED = 1 };
-static bool g_cta_pairs = true;  // atq_set_cta_pairs(): A/B switch for the cta_group::2 kernels
+static bool g_cta_pairs = true;   // atq_set_cta_pairs(): A/B switch for the cta_group::2 kernels
+static bool g_wide_pairs = true;  // bit 1 of the same switch: 256-wide single-buffered pair tiles for long contractions
 
 struct GemmParams {
   int64_t rows, cols, kdim;
@@ -126,7 +127,10 @@ struct GemmCfg {
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr bool kDual = (NUM_A + NUM_B > 2);
   static constexpr int kAccCols = (kDual ? 2 : 1) * BLOCK_N;
-  static constexpr int kTmemCols = 2 * kAccCols;  // double-buffered
+  // two tiles' accumulators (the MMA warp runs ahead of the epilogue) whenever they fit the 512 TMEM columns; the
+  // 256-wide dual-accumulator tile fills TMEM by itself: single-buffered, worthwhile for long contractions
+  static constexpr int kAccBufs = (2 * kAccCols <= 512) ? 2 : 1;
+  static constexpr int kTmemCols = kAccBufs * kAccCols;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "not enough shared memory for a 2-stage pipeline");
   static_assert(kTmemCols <= 512, "TMEM has 512 columns");
@@ -147,7 +151,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
                  const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                  const GemmParams p) {
   using Cfg = GemmCfg<NUM_A, NUM_B, BLOCK_N, BK, CTA2>;
-  static_assert(!(CTA2 && (B_PACKED || BK != 64 || BLOCK_N != 128)), "CTA pairs: 128-wide TMA-fed tiles only");
+  static_assert(!(CTA2 && (B_PACKED || BK != 64 || (BLOCK_N != 128 && BLOCK_N != 256))), "CTA pairs: 128 / 256-wide TMA-fed tiles only");
+  constexpr int kAccBufs = Cfg::kAccBufs;
   constexpr int kPairM = CTA2 ? 2 * BLOCK_M : BLOCK_M;  // rows of the tile a work item covers
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0u;
@@ -290,8 +295,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       uint32_t phase = 0;
       int it = 0;
       for (int w = work_first; w < num_work; w += work_step, ++it) {
-        const int a = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        const int a = it % kAccBufs;
+        const uint32_t aphase = (uint32_t)(it / kAccBufs) & 1u;
         mbar_wait(tmem_empty_bar(a), aphase ^ 1u);  // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
         // Two accumulators per tile when an operand has a lo part.  tcgen05 accumulates in fp32 with truncation:
@@ -419,8 +424,8 @@ __global__ void __launch_bounds__(gemm_threads(B_PACKED, BLOCK_N), 1)
       else mbar_arrive(tmem_empty_bar(a));
     };
     for (int w = work_first; w < num_work; w += work_step, ++it) {
-      const int a = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      const int a = it % kAccBufs;
+      const uint32_t aphase = (uint32_t)(it / kAccBufs) & 1u;
       int tm, tn;
       tile_mn(w % num_tiles, tm, tn);
       const int64_t n0 = (int64_t)tn * BLOCK_N;
@@ -820,11 +825,23 @@ static int dispatch_layout(const atq_bf16_operand* a, const atq_bf16_operand* b,
   // CTA pairs (cta_group::2) once the output has at least one 256-row tile per pair-column: halves the B-operand
   // shared-memory reads per flop of the 128-wide dual-accumulator tiles
   const bool pairs = g_cta_pairs && p.rows >= 256 && p.cols >= 128;
-#define ATQ_GO2(NA, NB) return launch_cfg<NA, NB, 128, EPI, false, LAYOUT, BLOCK_K, true>(a, b, p, stream, grid_used)
+#define ATQ_GO2(NA, NB, BN) return launch_cfg<NA, NB, BN, EPI, false, LAYOUT, BLOCK_K, true>(a, b, p, stream, grid_used)
   if (pairs) {
-    if (a2 && b2) ATQ_GO2(2, 2);
-    if (b2) ATQ_GO2(1, 2);
-    if (a2) ATQ_GO2(2, 1);
+    // long contractions: 256 x 256 pair tiles (half the operand bytes per flop; the two 256-wide accumulators fill
+    // TMEM, so the epilogue is not overlapped -- it is < 15 % of a tile from ~32 k-blocks on)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int64_t kb = (p.kdim + BLOCK_K - 1) / BLOCK_K / (p.splits > 1 ? p.splits : 1);
+    const int64_t tiles256 = ((p.cols + 255) / 256) * ((p.rows + 255) / 256) * (p.splits > 1 ? p.splits : 1);
+    const bool wide = g_wide_pairs && kb >= 32 && p.cols >= 256 && tiles256 * 2 >= sm_count(dev) / 2;
+    if (wide) {
+      if (a2 && b2) ATQ_GO2(2, 2, 256);
+      if (b2) ATQ_GO2(1, 2, 256);
+      if (a2) ATQ_GO2(2, 1, 256);
+    }
+    if (a2 && b2) ATQ_GO2(2, 2, 128);
+    if (b2) ATQ_GO2(1, 2, 128);
+    if (a2) ATQ_GO2(2, 1, 128);
   }
 #undef ATQ_GO2
   if (a2 && b2) ATQ_GO(2, 2, 128);
@@ -872,8 +889,9 @@ using namespace atq;
 extern "C" {
 
 int atq_set_cta_pairs(int enabled) {
-  const int old = g_cta_pairs ? 1 : 0;
-  g_cta_pairs = enabled != 0;
+  const int old = (g_cta_pairs ? 1 : 0) | (g_wide_pairs ? 2 : 0);
+  g_cta_pairs = (enabled & 1) != 0;
+  g_wide_pairs = (enabled & 2) != 0 || enabled == 1;
   return old;
 }
 

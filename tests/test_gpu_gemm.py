@@ -354,3 +354,38 @@ def test_dw_split_k_masked_epilogue_long_contraction():
     assert abs(float(dalpha) - want) <= 1e-3 * abs(want) + 5e-2
     dw2, dalpha2 = eng.tgemm_dw_masked(ga + (1,), xa + (1,), m_out, k_in, n_tok, mask=mask.to(DEV), packed=packed)
     assert torch.equal(dw, dw2) and torch.equal(dalpha, dalpha2)  # bitwise reproducible
+
+
+def test_frozen_ternary_linear_is_quantized_once():
+    """TernaryLinear.weight never receives a gradient, so no optimizer step can change it: its operands
+    are built once, not once per step; a gradient reaching the weight (L1 regularisation, train.py:195-203) or a new
+    Parameter re-arms the per-step invalidation."""
+    import atq._native as nv
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(atq.TernaryLinear(64, 48), torch.nn.ReLU(), atq.TernaryLinear(48, 16)).to(DEV)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-2)
+    x = torch.randn(32, 64, device=DEV)
+    builds = []
+    orig = nv.call
+
+    def counting(name, *a):
+        if name == "atq_build_ternary_operands":
+            builds.append(name)
+        return orig(name, *a)
+    nv.call = counting
+    try:
+        for _ in range(4):
+            opt.zero_grad(set_to_none=True)
+            net(x).square().mean().backward()
+            opt.step()
+        assert len(builds) == 2, builds            # one build per layer, ever
+        assert net[0].weight.grad is None
+        # a gradient reaches the weight: from now on every optimizer step invalidates the operands
+        opt.zero_grad(set_to_none=True)
+        (net(x).square().mean() + 1e-3 * net[0].weight.abs().sum()).backward()
+        opt.step()
+        n0 = len(builds)
+        net(x)
+        assert len(builds) == n0 + 1
+    finally:
+        nv.call = orig
