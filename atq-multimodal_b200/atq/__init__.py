@@ -15,6 +15,7 @@ from ._engine import (set_gemm_mode, get_gemm_mode, set_ste, set_packed_gemm, pr
 from .attention import attention_core, supported as attention_core_supported
 from ._engine import rpb_ffn as fused_ffn, rpb_ffn_supported as fused_ffn_supported  # GELU + dropout fused into the FFN
 from ._engine import gated_residual, gated_residual_supported  # src + dropout(h) * gate in one pass
+from ._engine import layer_norm, layer_norm_supported  # LayerNorm that also leaves max|y| for the operand split after it
 from .contrastive import (HardNegativeMiningInfoNCE, ContrastiveLearningManager,
                           hard_negative_infonce)
 

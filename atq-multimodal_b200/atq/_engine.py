@@ -19,6 +19,7 @@ GEMM precision modes (every mode accumulates in fp32 in TMEM):
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 import os
 from typing import Optional
@@ -281,11 +282,36 @@ def split_bf16(x2: torch.Tensor, want_lo: bool, slot: Optional[torch.Tensor] = N
 _FUSED_MAX = int(nv.lib.atq_split_scaled_fused_max_elems())
 
 
+# Producers that already reduced max|y| while writing y (layer_norm) leave the finished scale slot here, keyed by the
+# output's memory; the operand split of that tensor then skips its own reduction pass.  A detached alias pins the memory
+# (so the address cannot be recycled under the key); the version counter catches in-place edits.
+_ABSMAX_HINTS: "collections.OrderedDict" = collections.OrderedDict()
+_ABSMAX_HINT_STATS = {"set": 0, "hit": 0}
+
+
+def _note_absmax(y: torch.Tensor, slot: torch.Tensor) -> None:
+    _ABSMAX_HINTS[(nv.device_index(y), y.data_ptr())] = (y.numel(), y._version, y.detach(), slot)
+    _ABSMAX_HINT_STATS["set"] += 1
+    while len(_ABSMAX_HINTS) > 4:
+        _ABSMAX_HINTS.popitem(last=False)
+
+
+def _known_absmax(x2: torch.Tensor) -> Optional[torch.Tensor]:
+    hit = _ABSMAX_HINTS.get((nv.device_index(x2), x2.data_ptr()))
+    if hit is None or hit[0] != x2.numel() or hit[1] != x2._version or not x2.is_contiguous():
+        return None
+    _ABSMAX_HINT_STATS["hit"] += 1
+    return hit[3]
+
+
 def split_scaled(x2: torch.Tensor, want_lo: bool = True):
     """Scaled-fp16 operand of a contiguous fp32 [rows, cols] tensor: one cluster kernel (max|x|, scale, split) for
     small tensors, the grid-level reduction followed by the streaming split otherwise."""
     rows, cols = x2.shape
     n = rows * cols
+    known = _known_absmax(x2) if _ABSMAX_HINTS else None
+    if known is not None:
+        return split_bf16(x2, want_lo, known)
     if _FUSED_SPLIT and n <= _FUSED_MAX and cols % 8 == 0 and x2.stride(0) == cols and x2.data_ptr() % 16 == 0:
         dev = nv.device_index(x2)
         hi = torch.empty((rows, cols), dtype=torch.float16, device=x2.device)
@@ -873,6 +899,61 @@ def gated_residual(src, h, g, dropout_p: float = 0.0, training: bool = True, see
     if p > 0.0 and seed is None:
         seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=src.device)
     return _GatedResidualFn.apply(src, h, g, p, seed if p > 0.0 else None)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """LayerNorm over the last dimension (the op in front of every ternary GEMM of the transformer block,
+    models/text_encoder.py:77,232,244): one pass forward that also leaves max|y| in a scale slot for the operand split
+    that follows, one pass backward with deterministic gamma / beta gradients."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, eps):
+        cols = x.shape[-1]
+        x2 = nv.require_f32(x, "input").reshape(-1, cols)
+        w_c = nv.require_f32(weight.detach(), "weight")
+        b_c = nv.require_f32(bias.detach(), "bias")
+        rows = x2.shape[0]
+        dev = nv.device_index(x2)
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x2.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x2.device)
+        slot = nv.new_slot(x2.device) if _use_f16() else None
+        nv.call("atq_layernorm_fwd", dev, x2.data_ptr(), w_c.data_ptr(), b_c.data_ptr(), rows, cols, float(eps), y.data_ptr(),
+                mean.data_ptr(), rstd.data_ptr(), nv.ptr(slot), nv.stream_ptr(dev))
+        ctx.save_for_backward(x2, w_c, mean, rstd)
+        out = y.view(x.shape)
+        if slot is not None:
+            _note_absmax(out, slot)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        x2, w_c, mean, rstd = ctx.saved_tensors
+        rows, cols = x2.shape
+        d2 = nv.require_f32(dout, "grad_output").reshape(rows, cols)
+        dev = nv.device_index(d2)
+        dx = torch.empty_like(x2)
+        dw = torch.empty(cols, dtype=torch.float32, device=d2.device)
+        db = torch.empty(cols, dtype=torch.float32, device=d2.device)
+        ws = nv.workspace(nv.lib.atq_workspace_bytes_layernorm_bwd(cols), d2.device)
+        nv.call("atq_layernorm_bwd", dev, d2.data_ptr(), x2.data_ptr(), w_c.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, cols,
+                dx.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(), nv.stream_ptr(dev))
+        return dx.view(dout.shape), dw, db, None
+
+
+def layer_norm_supported(x, weight, bias) -> bool:
+    cols = x.shape[-1] if x.dim() else 0
+    return (x.is_cuda and x.dtype == torch.float32 and weight is not None and bias is not None and x.numel() > 0
+            and 4 <= cols <= 1024 and cols % 4 == 0 and weight.numel() == cols and bias.numel() == cols)
+
+
+def layer_norm(x, weight, bias, eps: float = 1e-5):
+    """F.layer_norm(x, (cols,), weight, bias, eps) on the fused kernels (fp32, 4 <= cols <= 1024, cols % 4 == 0)."""
+    if not layer_norm_supported(x, weight, bias):
+        raise RuntimeError("atq.layer_norm: needs an fp32 CUDA tensor with 4 <= last dim <= 1024 (multiple of 4), affine weight and bias")
+    return _LayerNormFn.apply(x, weight, bias, eps)
 
 
 def ternary_linear(x, weight, alpha, bias, cache: LayerOperands, sparsity_target=0.3, threshold_factor=0.05):

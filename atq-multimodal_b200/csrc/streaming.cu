@@ -992,6 +992,159 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------
+// LayerNorm over the last dimension (the op either side of every ternary GEMM of the transformer block,
+// models/text_encoder.py:77,232,244; SURVEY 8f rank 2 "fuse LayerNorm into the GEMM prologue"): one warp per row, the
+// row lives in registers (cols <= 1024, cols % 4 == 0), fp32 two-pass statistics.
+//   forward : y = (x - mean) * rstd * gamma + beta, saves mean / rstd per row and folds max|y| into a scale slot, so
+//             the operand split that follows needs no reduction pass of its own;
+//   backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma, plus per-CTA partial column sums of
+//             dy * xhat and dy (reduced in fixed order by colsum_stage2_kernel: deterministic).
+// ------------------------------------------------------------------------------------
+constexpr int kLnVec = 8;  // float4 per lane: cols <= 32 * 8 * 4 = 1024
+
+__global__ void __launch_bounds__(kThreads)
+    layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows,
+                         int cols, float eps, float* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                         unsigned int* __restrict__ absmax_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (kThreads / 32);
+  const int nv = cols >> 2;  // float4 per row
+  const float inv_n = 1.f / (float)cols;
+  float amax = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); r < rows; r += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * cols);
+    float4 v[kLnVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < nv ? ldg_stream4(reinterpret_cast<const float*>(xr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sum) * inv_n;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+      if (lane + 32 * i < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c2 = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c2 * c2 + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_n + eps);
+    float4* yr = reinterpret_cast<float4*>(y + r * cols);
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        const float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                     (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+        yr[c] = o;
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+      }
+    }
+    if (lane == 0) {
+      mean_out[r] = mean;
+      rstd_out[r] = rstd;
+    }
+  }
+  if (absmax_bits != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    __shared__ float s_m[kThreads / 32];
+    if (lane == 0) s_m[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < kThreads / 32; ++i) amax = fmaxf(amax, s_m[i]);
+      atomicMax(absmax_bits, __float_as_uint(amax));
+    }
+  }
+}
+
+__global__ void scale_slot_finalize_kernel(float* slot, float bound_mul) {
+  unsigned int* bits = reinterpret_cast<unsigned int*>(slot);
+  float sc, inv;
+  pow2_scale_for(__uint_as_float(bits[0]) * bound_mul, sc, inv);
+  slot[1] = sc;
+  slot[2] = inv;
+  bits[0] = 0u;
+}
+
+__global__ void __launch_bounds__(kThreads)
+    layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ mean_in, const float* __restrict__ rstd_in, int64_t rows, int cols,
+                         float* __restrict__ dx, float* __restrict__ part_g, float* __restrict__ part_b) {
+  extern __shared__ float s_red[];  // [kThreads / 32][cols]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warps = (int64_t)gridDim.x * (kThreads / 32);
+  const int nv = cols >> 2;
+  const float inv_n = 1.f / (float)cols;
+  float4 ag[kLnVec], ab[kLnVec];  // this lane's running column sums of dy * xhat and dy
+#pragma unroll
+  for (int i = 0; i < kLnVec; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = (int64_t)blockIdx.x * (kThreads / 32) + wid; r < rows; r += warps) {
+    const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
+    const float4* xr = reinterpret_cast<const float4*>(x + r * cols);
+    const float4* gr = reinterpret_cast<const float4*>(dy + r * cols);
+    float4 xh[kLnVec], g[kLnVec];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        xh[i] = ldg_stream4(reinterpret_cast<const float*>(xr + c));
+        g[i] = ldg_stream4(reinterpret_cast<const float*>(gr + c));
+      } else {
+        xh[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        xh[i] = make_float4((xh[i].x - mean) * rstd, (xh[i].y - mean) * rstd, (xh[i].z - mean) * rstd, (xh[i].w - mean) * rstd);
+        ag[i].x += g[i].x * xh[i].x; ag[i].y += g[i].y * xh[i].y; ag[i].z += g[i].z * xh[i].z; ag[i].w += g[i].w * xh[i].w;
+        ab[i].x += g[i].x; ab[i].y += g[i].y; ab[i].z += g[i].z; ab[i].w += g[i].w;
+        g[i] = make_float4(g[i].x * gm.x, g[i].y * gm.y, g[i].z * gm.z, g[i].w * gm.w);
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      }
+    }
+    s1 = warp_sum(s1) * inv_n;
+    s2 = warp_sum(s2) * inv_n;
+    float4* dr = reinterpret_cast<float4*>(dx + r * cols);
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv)
+        dr[c] = make_float4(rstd * (g[i].x - s1 - xh[i].x * s2), rstd * (g[i].y - s1 - xh[i].y * s2),
+                            rstd * (g[i].z - s1 - xh[i].z * s2), rstd * (g[i].w - s1 - xh[i].w * s2));
+    }
+  }
+  // CTA-level column sums: the 8 warps' lanes own the same columns; fixed-order combine through shared memory
+  for (int pass = 0; pass < 2; ++pass) {
+    float4* mine = reinterpret_cast<float4*>(s_red + (size_t)wid * cols);
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) mine[c] = pass == 0 ? ag[i] : ab[i];
+    }
+    __syncthreads();
+    float* out = (pass == 0 ? part_g : part_b) + (size_t)blockIdx.x * cols;
+    for (int c = threadIdx.x; c < cols; c += kThreads) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kThreads / 32; ++w) t += s_red[(size_t)w * cols + c];
+      out[c] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // column sums (bias gradient): deterministic two-stage reduction
 // ------------------------------------------------------------------------------------
 // rows per CTA: 64 for short inputs (enough CTAs to hide latency), up to 512 for long ones
@@ -1518,6 +1671,55 @@ int atq_adamw_multi(int device, const void* table, const int* chunk_tensor, cons
                                                weight_decay, step);
   ATQ_LAUNCH_CHECK();
   adamw_advance_kernel<<<1, 1, 0, stream>>>(step);
+  ATQ_LAUNCH_CHECK();
+  return ATQ_OK;
+}
+
+static inline int layernorm_grid(int device, int64_t rows) {
+  int64_t need = (rows + (kThreads / 32) - 1) / (kThreads / 32);
+  const int64_t cap = (int64_t)sm_count(device) * 2;
+  return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+
+size_t atq_workspace_bytes_layernorm_bwd(int64_t cols) { return (size_t)2 * 2 * 256 * (size_t)cols * sizeof(float); }
+
+int atq_layernorm_fwd(int device, const float* x, const float* gamma, const float* beta, int64_t rows, int64_t cols, float eps, float* y,
+                      float* mean_out, float* rstd_out, float* out_scale_slot, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(x && gamma && beta && y && mean_out && rstd_out && rows > 0, "null pointer or rows <= 0");
+  ATQ_CHECK_ARG(cols >= 4 && cols <= 32 * kLnVec * 4 && (cols % 4) == 0, "needs 4 <= cols <= 1024, cols % 4 == 0");
+  ATQ_CHECK_ARG(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "needs 16-byte aligned contiguous tensors");
+  ATQ_ENSURE_DEVICE(device);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  layernorm_fwd_kernel<<<layernorm_grid(device, rows), kThreads, 0, stream>>>(x, gamma, beta, rows, (int)cols, eps, y, mean_out, rstd_out,
+                                                                              reinterpret_cast<unsigned int*>(out_scale_slot));
+  ATQ_LAUNCH_CHECK();
+  if (out_scale_slot != nullptr) {
+    scale_slot_finalize_kernel<<<1, 1, 0, stream>>>(out_scale_slot, 1.f);
+    ATQ_LAUNCH_CHECK();
+  }
+  return ATQ_OK;
+}
+
+int atq_layernorm_bwd(int device, const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int64_t rows,
+                      int64_t cols, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes, atq_stream_t stream_) {
+  ATQ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && rows > 0, "null pointer or rows <= 0");
+  ATQ_CHECK_ARG(cols >= 4 && cols <= 32 * kLnVec * 4 && (cols % 4) == 0, "needs 4 <= cols <= 1024, cols % 4 == 0");
+  ATQ_CHECK_ARG(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma), "needs 16-byte aligned contiguous tensors");
+  ATQ_ENSURE_DEVICE(device);
+  const int grid = layernorm_grid(device, rows);
+  if (ws == nullptr || ws_bytes < (size_t)2 * grid * cols * sizeof(float)) {
+    set_error("atq_layernorm_bwd: workspace too small (atq_workspace_bytes_layernorm_bwd)");
+    return ATQ_EWORKSPACE;
+  }
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* part_g = reinterpret_cast<float*>(ws);
+  float* part_b = part_g + (size_t)grid * cols;
+  const size_t smem = (size_t)(kThreads / 32) * cols * sizeof(float);
+  layernorm_bwd_kernel<<<grid, kThreads, smem, stream>>>(dy, x, gamma, mean, rstd, rows, (int)cols, dx, part_g, part_b);
+  ATQ_LAUNCH_CHECK();
+  colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>(part_g, grid, cols, dgamma);
+  ATQ_LAUNCH_CHECK();
+  colsum_stage2_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>(part_b, grid, cols, dbeta);
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }

@@ -285,6 +285,18 @@ int atq_gelu_dropout_bwd_split_colsum(int device, const float* g, const float* y
                                       const unsigned long long* seed, uint16_t* hi, uint16_t* lo, float* colsum_out,
                                       void* ws, size_t ws_bytes, const float* scale_slot, atq_stream_t stream);
 
+/* LayerNorm over the last dimension of a contiguous fp32 [rows, cols] tensor (4 <= cols <= 1024, cols % 4 == 0), the op
+ * in front of every ternary GEMM of the transformer block (models/text_encoder.py:77,232,244).  forward saves mean / rstd
+ * per row and, when out_scale_slot != NULL (zero slot[0] on entry), leaves {s, 1/s} for y as a scaled-fp16 operand in
+ * slot[1..2] (the operand split that follows needs no reduction pass).  backward: dx, dgamma, dbeta (deterministic
+ * two-stage column sums); ws >= atq_workspace_bytes_layernorm_bwd(cols). */
+int atq_layernorm_fwd(int device, const float* x, const float* gamma, const float* beta, int64_t rows, int64_t cols, float eps,
+                      float* y, float* mean_out, float* rstd_out, float* out_scale_slot /* nullable */, atq_stream_t stream);
+size_t atq_workspace_bytes_layernorm_bwd(int64_t cols);
+int atq_layernorm_bwd(int device, const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                      int64_t rows, int64_t cols, float* dx, float* dgamma, float* dbeta, void* ws, size_t ws_bytes,
+                      atq_stream_t stream);
+
 /* Gated residual of the ternary transformer block (models/text_encoder.py:238-249):
  *   out = src + dropout(h) * g   with g = sigmoid(gate) a device scalar; n % 4 == 0, contiguous tensors.
  * backward: dh = dout * g * keep/(1-p), dgate = sum(dout .* dropout(h)) (deterministic two-stage sum); d(src) = dout. */

@@ -13,6 +13,7 @@ tests/test_workloads.py checks them against the reference's own models in the bu
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 
 import torch
@@ -30,6 +31,15 @@ def _lengths_to_mask(lengths, batch, seq, device):
 FUSED_ATTENTION_CORE = True
 # True: linear2(dropout(gelu(linear1(h)))) of a TernaryBlock runs through atq.fused_ffn when both layers are RPB
 FUSED_FFN = True
+FUSED_LAYERNORM = os.environ.get("ATQ_FUSED_LAYERNORM", "1") == "1"
+
+
+def _norm(owner, mod, x):
+    """nn.LayerNorm `mod` on the B200 package's fused LayerNorm kernels (which also leave max|y| for the operand split
+    of the GEMM that follows) when they apply, torch's otherwise."""
+    if FUSED_LAYERNORM and owner._ln is not None and owner._ln_ok(x, mod.weight, mod.bias):
+        return owner._ln(x, mod.weight, mod.bias, mod.eps)
+    return mod(x)
 # True: RetrievalModel instances with `parallel_towers = True` run the text tower on a side stream
 PARALLEL_TOWERS = True
 
@@ -58,6 +68,8 @@ class TernaryAttention(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.pre_layer_norm = nn.LayerNorm(embed_dim)
         # the B200 package exports a fused attention core (atq/attention.py); the CPU oracle layers do not
+        self._ln = getattr(layers, "layer_norm", None)
+        self._ln_ok = getattr(layers, "layer_norm_supported", None)
         self._core = getattr(layers, "attention_core", None)
         self._core_ok = getattr(layers, "attention_core_supported", None)
 
@@ -68,7 +80,7 @@ class TernaryAttention(nn.Module):
                 m.sparsity_target = s
 
     def forward(self, query, key, value, key_padding_mask=None):
-        query = self.pre_layer_norm(query)
+        query = _norm(self, self.pre_layer_norm, query)
         b = query.size(0)
         q, k, v = self.q_proj(query), self.k_proj(key), self.v_proj(value)
         if (FUSED_ATTENTION_CORE and self._core is not None and q.is_cuda
@@ -117,6 +129,8 @@ class TernaryBlock(nn.Module):
         self.dropout1 = nn.Dropout(dropout)
         self.dropout2 = nn.Dropout(dropout)
         self.gate = nn.Parameter(torch.ones(1) * 0.8)
+        self._ln = getattr(layers, "layer_norm", None)
+        self._ln_ok = getattr(layers, "layer_norm_supported", None)
         self._ffn = getattr(layers, "fused_ffn", None)            # B200 package only
         self._ffn_ok = getattr(layers, "fused_ffn_supported", None)
         self._gres = getattr(layers, "gated_residual", None)
@@ -130,11 +144,11 @@ class TernaryBlock(nn.Module):
                 m.sparsity_target = s
 
     def forward(self, src, key_padding_mask=None):
-        h = self.norm1(src)
+        h = _norm(self, self.norm1, src)
         h = self.self_attn(h, h, h, key_padding_mask=key_padding_mask)
         gate = torch.sigmoid(self.gate)
         src = self._residual(src, h, gate, self.dropout1)
-        h = self.norm2(src)
+        h = _norm(self, self.norm2, src)
         if FUSED_FFN and self._ffn is not None and self._ffn_ok(self.linear1, self.linear2, h):
             # own kernels: gelu + dropout + operand split of the hidden tensor in one pass per direction
             h = self._ffn(self.linear1, self.linear2, h, self.dropout.p, self.training)
