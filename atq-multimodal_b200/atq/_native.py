@@ -14,7 +14,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libatq_sm100.so")
+_LIB_PATH = os.environ.get("ATQ_SM100_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libatq_sm100.so")
 if not os.path.exists(_LIB_PATH):
     raise ImportError(
         f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

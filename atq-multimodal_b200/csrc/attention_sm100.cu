@@ -24,6 +24,13 @@
 
 namespace atq {
 
+#ifdef ATQ_ATTN_PROF
+__device__ long long g_attn_prof[64];
+#define ATTN_PROF(i) do { if (blockIdx.x == 200 && threadIdx.x == 0) g_attn_prof[(i)] = clock64(); } while (0)
+#else
+#define ATTN_PROF(i) do { } while (0)
+#endif
+
 constexpr int kHd = 64;          // head dim
 constexpr int kAttThreads = 256; // 8 warps: warps w and w+4 share TMEM lane quarter w & 3 and split the columns
 constexpr int kTileBytes = 128 * 128;  // 128 rows x 64 bf16
@@ -64,42 +71,51 @@ __device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w
 __device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
 // fp32 [rows_valid x 64] (row pitch in floats, 16-byte aligned rows) -> bf16 hi (+ lo) tiles of rows_total
-// swizzled 128-byte rows; rows >= rows_valid become zeros.  8 threads per row (32 B of fp32 each).  All global
-// loads of up to PASSES row passes (PASSES x 32 rows) are in flight before the first conversion, so a 128-row
-// tile (PASSES = 4) or a 256-row K / V tile (PASSES = 8) costs ONE memory round trip.
-__device__ __forceinline__ void convert_store_row(const float4& a, const float4& b, int r, int c, bool lo, uint32_t s_hi, uint32_t s_lo) {
-  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = pack2_bf16(x[2 * j], x[2 * j + 1]);
-    l[j] = pack2_bf16(x[2 * j] - bf16lo_f(h[j]), x[2 * j + 1] - bf16hi_f(h[j]));
+// swizzled 128-byte rows; rows >= rows_valid become zeros.  8 threads per row: thread c loads the float4 at columns
+// 4c and 32 + 4c, so every warp-level load covers whole 128-byte row segments (no half-used sectors), and stores the
+// two 8-byte halves of the bf16 chunks they fall into.  All global loads of up to PASSES row passes (PASSES x 32 rows)
+// are in flight before the first conversion, so a 128-row tile (PASSES = 4) or a 256-row K / V tile (PASSES = 8) costs
+// ONE memory round trip.
+__device__ __forceinline__ void convert_store_half(const float4& a, int r, int chunk, int sub, bool lo, uint32_t s_hi, uint32_t s_lo) {
+  const uint32_t h0 = pack2_bf16(a.x, a.y), h1 = pack2_bf16(a.z, a.w);
+  const uint32_t off = (uint32_t)r * 128u + (((uint32_t)chunk ^ ((uint32_t)r & 7u)) << 4) + (uint32_t)sub;
+  st_shared_v2(s_hi + off, h0, h1);
+  if (lo) {
+    const uint32_t l0 = pack2_bf16(a.x - bf16lo_f(h0), a.y - bf16hi_f(h0));
+    const uint32_t l1 = pack2_bf16(a.z - bf16lo_f(h1), a.w - bf16hi_f(h1));
+    st_shared_v2(s_lo + off, l0, l1);
   }
-  const uint32_t off = (uint32_t)r * 128u + (((uint32_t)c ^ ((uint32_t)r & 7u)) << 4);
-  st_shared_v4(s_hi + off, make_uint4(h[0], h[1], h[2], h[3]));
-  if (lo) st_shared_v4(s_lo + off, make_uint4(l[0], l[1], l[2], l[3]));
+}
+__device__ __forceinline__ void convert_store_row(const float4& a, const float4& b, int r, int c, bool lo, uint32_t s_hi, uint32_t s_lo) {
+  convert_store_half(a, r, c >> 1, (c & 1) * 8, lo, s_hi, s_lo);
+  convert_store_half(b, r, 4 + (c >> 1), (c & 1) * 8, lo, s_hi, s_lo);
 }
 
 template <bool LO, int PASSES = 4>
 __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t pitch, int rows_valid, int rows_total,
                                            uint32_t s_hi, uint32_t s_lo, int hd) {
   const int c = threadIdx.x & 7;
-  if (8 * c >= hd) rows_valid = 0;  // head dims < 64: the missing 8-column chunks are zero padding
+  const bool va = 4 * c < hd, vb = 32 + 4 * c < hd;  // head dims < 64: the missing columns are zero padding
   constexpr int kRowsPerPass = kAttThreads / 8;  // 32
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int r0 = threadIdx.x >> 3; r0 < rows_total; r0 += PASSES * kRowsPerPass) {
     float4 a[PASSES], b[PASSES];
 #pragma unroll
     for (int i = 0; i < PASSES; ++i) {
       const int r = r0 + i * kRowsPerPass;
-      if (r < rows_valid) {
-        const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * pitch + 8 * c);
-        a[i] = __ldg(p);
-        b[i] = __ldg(p + 1);
-      } else {
-        a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        b[i] = a[i];
-      }
+      const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * pitch) + c;
+      a[i] = (r < rows_valid && va) ? __ldg(p) : zero;
+      b[i] = (r < rows_valid && vb) ? __ldg(p + 8) : zero;
     }
+#ifdef ATQ_ATTN_PROF
+    if (PASSES == 8) {  // when did the last load land?
+      float chk = 0.f;
+#pragma unroll
+      for (int i = 0; i < PASSES; ++i) chk += a[i].x + b[i].w;
+      if (chk == 1.2345e30f) g_attn_prof[63] = 1;
+      if (blockIdx.x == 200 && threadIdx.x == 0) g_attn_prof[32 + (g_attn_prof[62]++ & 7)] = clock64();
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < PASSES; ++i) {
       const int r = r0 + i * kRowsPerPass;
@@ -114,25 +130,76 @@ __device__ __forceinline__ void stage_two_tiles(const float* __restrict__ src0, 
                                                 const float* __restrict__ src1, int64_t pitch1, uint32_t s_hi1, uint32_t s_lo1,
                                                 int rows_valid, int hd) {
   const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
-  if (8 * c >= hd) rows_valid = 0;
+  const bool va = 4 * c < hd, vb = 32 + 4 * c < hd;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 a0[4], b0[4], a1[4], b1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + i * 32;
-    if (r < rows_valid) {
-      const float4* p0 = reinterpret_cast<const float4*>(src0 + (int64_t)r * pitch0 + 8 * c);
-      const float4* p1 = reinterpret_cast<const float4*>(src1 + (int64_t)r * pitch1 + 8 * c);
-      a0[i] = __ldg(p0); b0[i] = __ldg(p0 + 1);
-      a1[i] = __ldg(p1); b1[i] = __ldg(p1 + 1);
-    } else {
-      a0[i] = b0[i] = a1[i] = b1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    const float4* p0 = reinterpret_cast<const float4*>(src0 + (int64_t)r * pitch0) + c;
+    const float4* p1 = reinterpret_cast<const float4*>(src1 + (int64_t)r * pitch1) + c;
+    a0[i] = (r < rows_valid && va) ? __ldg(p0) : zero;
+    b0[i] = (r < rows_valid && vb) ? __ldg(p0 + 8) : zero;
+    a1[i] = (r < rows_valid && va) ? __ldg(p1) : zero;
+    b1[i] = (r < rows_valid && vb) ? __ldg(p1 + 8) : zero;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = r0 + i * 32;
     convert_store_row(a0[i], b0[i], r, c, LO, s_hi0, s_lo0);
     convert_store_row(a1[i], b1[i], r, c, LO, s_hi1, s_lo1);
+  }
+}
+
+// backward: the Q and dO tiles of one query tile travel through registers in two steps, so that the global loads of the
+// NEXT (key tile, query tile) iteration are in flight while the tensor cores work on the current one.  With `with_o`,
+// delta[r] = sum_d dO[r, d] * O[r, d] over this head comes from the SAME dO registers and an O load with the same
+// mapping (the 8 threads of a row reduce by shuffle).
+struct QdoRegs {
+  float4 a0[4], b0[4], a1[4], b1[4], oa[4], ob[4];
+};
+__device__ __forceinline__ void load_q_do(QdoRegs& R, const float* __restrict__ qg, int64_t q_pitch, const float* __restrict__ dg,
+                                          int64_t do_pitch, const float* __restrict__ og, int64_t o_pitch, bool with_o, int rows_valid,
+                                          int hd) {
+  const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+  const bool va = 4 * c < hd, vb = 32 + 4 * c < hd;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + i * 32;
+    const bool ok = r < rows_valid;
+    const float4* p0 = reinterpret_cast<const float4*>(qg + (int64_t)r * q_pitch) + c;
+    const float4* p1 = reinterpret_cast<const float4*>(dg + (int64_t)r * do_pitch) + c;
+    R.a0[i] = (ok && va) ? __ldg(p0) : zero;
+    R.b0[i] = (ok && vb) ? __ldg(p0 + 8) : zero;
+    R.a1[i] = (ok && va) ? __ldg(p1) : zero;
+    R.b1[i] = (ok && vb) ? __ldg(p1 + 8) : zero;
+    if (with_o) {
+      const float4* p2 = reinterpret_cast<const float4*>(og + (int64_t)r * o_pitch) + c;
+      R.oa[i] = (ok && va) ? __ldg(p2) : zero;
+      R.ob[i] = (ok && vb) ? __ldg(p2 + 8) : zero;
+    }
+  }
+}
+template <bool LO>
+__device__ __forceinline__ void store_q_do(const QdoRegs& R, uint32_t s_qh, uint32_t s_ql, uint32_t s_dh, uint32_t s_dl, float* s_delta) {
+  const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+  if (s_delta != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float d = (R.a1[i].x * R.oa[i].x + R.a1[i].y * R.oa[i].y) + (R.a1[i].z * R.oa[i].z + R.a1[i].w * R.oa[i].w) +
+                (R.b1[i].x * R.ob[i].x + R.b1[i].y * R.ob[i].y) + (R.b1[i].z * R.ob[i].z + R.b1[i].w * R.ob[i].w);
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      if (c == 0) s_delta[r0 + i * 32] = d;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + i * 32;
+    convert_store_row(R.a0[i], R.b0[i], r, c, LO, s_qh, s_ql);
+    convert_store_row(R.a1[i], R.b1[i], r, c, LO, s_dh, s_dl);
   }
 }
 
@@ -185,6 +252,30 @@ __device__ __forceinline__ void store_row32_bf16(uint32_t base, int row, int ch,
   }
 }
 
+// One [128 x 64] fp32 accumulator tile (thread = row, columns [32 half, +32) in o[], scaled by `mul`) -> global rows
+// gbase + r * pitch (r < rows_valid, columns < hd) through a 32 KB swizzled shared-memory tile, so that every warp-level
+// global store covers two whole row segments instead of 32 rows x 16 bytes.  Contains a block barrier.
+__device__ __forceinline__ void store_tile_coalesced(uint32_t s_stage, const float (&o)[32], float mul, int row, int half,
+                                                     float* __restrict__ gbase, int64_t pitch, int rows_valid, int hd) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t slot = (uint32_t)(half * 8 + j) ^ ((uint32_t)row & 7u);
+    st_shared_f4(s_stage + (uint32_t)row * 256u + (slot << 4), o[4 * j] * mul, o[4 * j + 1] * mul, o[4 * j + 2] * mul, o[4 * j + 3] * mul);
+  }
+  __syncthreads();
+  const int l = threadIdx.x & 31, w = threadIdx.x >> 5, jj = l & 15;
+  if (4 * jj < hd) {
+#pragma unroll
+    for (int pass = 0; pass < 128 / (2 * (kAttThreads / 32)); ++pass) {
+      const int r = pass * 2 * (kAttThreads / 32) + w * 2 + (l >> 4);
+      if (r < rows_valid) {
+        const float4 v = ld_shared_f4(s_stage + (uint32_t)r * 256u + (((uint32_t)jj ^ ((uint32_t)r & 7u)) << 4));
+        *reinterpret_cast<float4*>(gbase + (int64_t)r * pitch + 4 * jj) = v;
+      }
+    }
+  }
+}
+
 // key validity bits (key < L and not padded) for up to 256 keys -> s_valid[8]
 __device__ __forceinline__ void build_valid_bits(const AttnParams& p, int b, uint32_t* s_valid) {
   const int k = (int)threadIdx.x;  // kAttThreads == 256
@@ -219,6 +310,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int L = p.L;
 
+  ATTN_PROF(0);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -227,16 +319,23 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   build_valid_bits(p, b, s_valid);
   const float* kg = p.k + (int64_t)b * L * p.k_pitch + h * p.hd;
   const float* vg = p.v + (int64_t)b * L * p.v_pitch + h * p.hd;
+  ATTN_PROF(20);
   if (lo) {
     stage_tile<true, 8>(kg, p.k_pitch, L, NK, s_kh, s_kl, p.hd);
+    ATTN_PROF(21);
     stage_tile<true, 8>(vg, p.v_pitch, L, NK, s_vh, s_vl, p.hd);
+    ATTN_PROF(22);
   } else {
     stage_tile<false, 8>(kg, p.k_pitch, L, NK, s_kh, 0, p.hd);
     stage_tile<false, 8>(vg, p.v_pitch, L, NK, s_vh, 0, p.hd);
   }
+#ifdef ATQ_ATTN_PROF
+  if (blockIdx.x == 200 && (threadIdx.x & 31) == 0) g_attn_prof[24 + warp] = clock64();
+#endif
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  ATTN_PROF(1);
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
   const uint32_t t_s = tmem, t_o = tmem + 256u;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -246,14 +345,31 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
   uint32_t phase = 0;
 
+  // the Q tile travels through registers: the loads of the next query tile are issued while the tensor cores and the
+  // softmax work on the current one
+  float4 qa[4], qb[4];
+  auto issue_q_loads = [&](int q0n) {
+    const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+    const bool va = 4 * c < p.hd, vb = 32 + 4 * c < p.hd;
+    const int valid = (L - q0n) < 128 ? (L - q0n) : 128;
+    const float* qg = p.q + ((int64_t)b * L + q0n) * p.q_pitch + h * p.hd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + i * 32;
+      const float4* src = reinterpret_cast<const float4*>(qg + (int64_t)r * p.q_pitch) + c;
+      qa[i] = (r < valid && va) ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qb[i] = (r < valid && vb) ? __ldg(src + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  issue_q_loads(0);
   for (int q0 = 0; q0 < L; q0 += 128) {
     const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
-    const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * p.hd;
-    if (lo) stage_tile<true>(qg, p.q_pitch, q_valid, 128, s_qh, s_ql, p.hd);
-    else stage_tile<false>(qg, p.q_pitch, q_valid, 128, s_qh, 0, p.hd);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) convert_store_row(qa[i], qb[i], (threadIdx.x >> 3) + i * 32, threadIdx.x & 7, lo, s_qh, s_ql);
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
+    ATTN_PROF(2 + (q0 >> 7) * 8);
     if (threadIdx.x == 0) {
       tcgen05_fence_after();
       const uint32_t idesc = make_idesc_rt(NK, false, false);
@@ -269,9 +385,11 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       }
       umma_commit(bar);
     }
+    if (q0 + 128 < L) issue_q_loads(q0 + 128);
     mbar_wait(bar, phase);
     phase ^= 1u;
     tcgen05_fence_after();
+    ATTN_PROF(3 + (q0 >> 7) * 8);
 
     // ---- softmax: query q0 + row; this warp covers key chunks [ch_lo, ch_hi) ----
     const uint32_t t_row = t_s + lane_off;
@@ -294,6 +412,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
     m = fmaxf(s_red[0][row], s_red[1][row]);
     if (m == -INFINITY) m = 0.f;  // every key masked: probabilities are all zero below
     __syncthreads();              // s_red is reused for the row sums
+    ATTN_PROF(4 + (q0 >> 7) * 8);
     const float mc = m * c2;
     const uint32_t row_key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * L + q0 + row));
     float sum = 0.f;
@@ -328,6 +447,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
     fence_proxy_async();
     tcgen05_fence_before();
     __syncthreads();
+    ATTN_PROF(5 + (q0 >> 7) * 8);
     if (threadIdx.x == 0) {
       tcgen05_fence_after();
       const uint32_t idesc = make_idesc_rt(kHd, false, true);
@@ -349,6 +469,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
     mbar_wait(bar, phase);
     phase ^= 1u;
     tcgen05_fence_after();
+    ATTN_PROF(6 + (q0 >> 7) * 8);
     if (lo) {
       // second pass through the same P buffer: P_lo (a single bf16 P leaves ~3e-3 absolute error in P V)
       for (int ch = ch_lo; ch < ch_hi; ++ch) {
@@ -359,6 +480,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       fence_proxy_async();
       tcgen05_fence_before();
       __syncthreads();
+      ATTN_PROF(7 + (q0 >> 7) * 8);
       if (threadIdx.x == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc_rt(kHd, false, true);
@@ -372,25 +494,23 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       mbar_wait(bar, phase);
       phase ^= 1u;
       tcgen05_fence_after();
+      ATTN_PROF(8 + (q0 >> 7) * 8);
     }
 
     // ---- epilogue: normalise and store; this warp writes output columns [32 half, 32 half + 32) ----
     const float inv = sum > 0.f ? 1.f / sum : 0.f;
     const int q = q0 + row;
     {
+      // staging tile: the Q tile (parity: hi + lo; fast: hi + the first P atom), dead once the last P V MMA has completed
       float o[32];
       ld_row32(t_o + lane_off + (uint32_t)(half * 32), o);
-      if (q < L) {
-        float4* dst = reinterpret_cast<float4*>(p.out + ((int64_t)b * L + q) * p.out_pitch + h * p.hd + half * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (half * 32 + 4 * j < p.hd) dst[j] = make_float4(o[4 * j] * inv, o[4 * j + 1] * inv, o[4 * j + 2] * inv, o[4 * j + 3] * inv);
-      }
+      store_tile_coalesced(s_qh, o, inv, row, half, p.out + ((int64_t)b * L + q0) * p.out_pitch + h * p.hd, p.out_pitch, q_valid, p.hd);
     }
     if (half == 0 && q < L && p.lse != nullptr) p.lse[(int64_t)bh * L + q] = sum > 0.f ? m * p.scale + logf(sum) : -INFINITY;
     tcgen05_fence_before();
     __syncthreads();  // TMEM, s_red and the Q / P tiles are reused by the next query tile
     tcgen05_fence_after();
+    ATTN_PROF(9 + (q0 >> 7) * 8);
   }
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
@@ -401,7 +521,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
 // shared memory (1024-aligned 16 KB tiles): K hi, K lo, V hi, V lo, Q hi, Q lo, dO hi, dO lo, then P, dS hi and
 // dS lo (two 64-key atoms each; dS carries a lo part because dQ / dK are sums of dS-weighted rows and a single
 // bf16 dS leaves ~3e-3 absolute error, above the 1e-3 tolerance).
-// TMEM columns: S [0,128) dP [128,256) dQ [256,320) dK [320,384) dV [384,448).
+// TMEM columns: S [0,128) dP [128,256) dQ tile 0 [256,320) dQ tile 1 [320,384) dK [384,448) dV [448,512).
 __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -413,7 +533,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
   __shared__ __align__(8) unsigned long long s_bar;
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_valid[8];
-  __shared__ float s_red[2][128];  // partial delta of the two column halves
+  __shared__ float s_delta[2][128];  // delta of both query tiles (written on the first key tile)
   const uint32_t bar = smem_u32(&s_bar);
   const int warp = threadIdx.x >> 5;
   const int half = warp >> 2;
@@ -421,6 +541,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
   const int bh = blockIdx.x, b = bh / p.H, h = bh % p.H;
   const int L = p.L;
 
+  ATTN_PROF(0);
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_barrier_init();
@@ -431,12 +552,20 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&s_tmem);
-  const uint32_t t_s = tmem, t_dp = tmem + 128u, t_dq = tmem + 256u, t_dk = tmem + 320u, t_dv = tmem + 384u;
+  // dQ of both query tiles stays in TMEM across the key tiles (no read-modify-write of dq in global memory)
+  const uint32_t t_s = tmem, t_dp = tmem + 128u, t_dq0 = tmem + 256u, t_dk = tmem + 384u, t_dv = tmem + 448u;
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const unsigned long long seed = p.seed != nullptr ? *p.seed : 0ull;
   const float c2 = p.scale * 1.4426950408889634f;
   uint32_t phase = 0;
 
+  QdoRegs R;
+  auto issue_q_do_loads = [&](int k0n, int q0n) {
+    const int64_t r0g = (int64_t)b * L + q0n;
+    load_q_do(R, p.q + r0g * p.q_pitch + h * p.hd, p.q_pitch, p.dout + r0g * p.do_pitch + h * p.hd, p.do_pitch,
+              p.o + r0g * p.o_pitch + h * p.hd, p.o_pitch, k0n == 0, (L - q0n) < 128 ? (L - q0n) : 128, p.hd);
+  };
+  issue_q_do_loads(0, 0);
   for (int k0 = 0; k0 < L; k0 += 128) {
     const int k_valid = (L - k0) < 128 ? (L - k0) : 128;
     const float* kg = p.k + ((int64_t)b * L + k0) * p.k_pitch + h * p.hd;
@@ -444,38 +573,21 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
     if (lo) stage_two_tiles<true>(kg, p.k_pitch, s_kh, s_kl, vg, p.v_pitch, s_vh, s_vl, k_valid, p.hd);
     else stage_two_tiles<false>(kg, p.k_pitch, s_kh, 0, vg, p.v_pitch, s_vh, 0, k_valid, p.hd);
     for (int q0 = 0; q0 < L; q0 += 128) {
-      const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
-      const float* qg = p.q + ((int64_t)b * L + q0) * p.q_pitch + h * p.hd;
-      const float* dg = p.dout + ((int64_t)b * L + q0) * p.do_pitch + h * p.hd;
-      // delta = sum_d dO[q,d] * O[q,d] over this head (row-sum of P .* dP): each column half adds 32 columns.
-      // Its loads are issued before the tile staging so that their latency hides behind the conversions.
+      // the Q / dO (/ O) registers of this iteration were loaded during the previous iteration's MMA wait.
+      // delta = sum_d dO[q,d] * O[q,d] over this head (row-sum of P .* dP) is computed on the first key tile and kept in
+      // shared memory for the later ones
       const int q = q0 + row;
       const bool q_ok = q < L;
-      float4 dx[8], dy[8];
-      if (q_ok) {
-        const float4* po = reinterpret_cast<const float4*>(p.o + ((int64_t)b * L + q) * p.o_pitch + h * p.hd + half * 32);
-        const float4* pd = reinterpret_cast<const float4*>(p.dout + ((int64_t)b * L + q) * p.do_pitch + h * p.hd + half * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (half * 32 + 4 * j < p.hd) { dx[j] = __ldg(po + j); dy[j] = __ldg(pd + j); }
-          else { dx[j] = make_float4(0.f, 0.f, 0.f, 0.f); dy[j] = dx[j]; }
-        }
-      }
       const float lse_q = q_ok ? __ldg(p.lse + (int64_t)bh * L + q) : 0.f;
-      if (lo) stage_two_tiles<true>(qg, p.q_pitch, s_qh, s_ql, dg, p.do_pitch, s_dh, s_dl, q_valid, p.hd);
-      else stage_two_tiles<false>(qg, p.q_pitch, s_qh, 0, dg, p.do_pitch, s_dh, 0, q_valid, p.hd);
       {
-        float d = 0.f;
-        if (q_ok) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            d += (dx[j].x * dy[j].x + dx[j].y * dy[j].y) + (dx[j].z * dy[j].z + dx[j].w * dy[j].w);
-        }
-        s_red[half][row] = d;
+        float* sd = k0 == 0 ? s_delta[q0 >> 7] : nullptr;
+        if (lo) store_q_do<true>(R, s_qh, s_ql, s_dh, s_dl, sd);
+        else store_q_do<false>(R, s_qh, 0, s_dh, 0, sd);
       }
       fence_proxy_async();
       tcgen05_fence_before();
       __syncthreads();
+      ATTN_PROF(1 + ((k0 >> 7) * 2 + (q0 >> 7)) * 8);
       if (threadIdx.x == 0) {
         tcgen05_fence_after();
         const uint32_t idesc = make_idesc_rt(128, false, false);
@@ -495,12 +607,13 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         }
         umma_commit(bar);
       }
-      const float delta = s_red[0][row] + s_red[1][row];
+      const float delta = s_delta[q0 >> 7][row];
       const float lse2 = lse_q * 1.4426950408889634f;
       const uint32_t row_key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * L + q));
       mbar_wait(bar, phase);
       phase ^= 1u;
       tcgen05_fence_after();
+      ATTN_PROF(2 + ((k0 >> 7) * 2 + (q0 >> 7)) * 8);
 
       // ---- query q0 + row, key chunks [2 half, 2 half + 2): P (after dropout) and dS ----
 #pragma unroll 1
@@ -544,13 +657,15 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
       fence_proxy_async();
       tcgen05_fence_before();
       __syncthreads();
+      ATTN_PROF(3 + ((k0 >> 7) * 2 + (q0 >> 7)) * 8);
       if (threadIdx.x == 0) {
         tcgen05_fence_after();
         const uint32_t idesc_q = make_idesc_rt(kHd, false, true);  // A K-major (dS), B MN-major (K tile)
         const uint32_t idesc_t = make_idesc_rt(kHd, true, true);   // A MN-major (dS^T / P^T), B MN-major (Q / dO)
         const int nt = lo ? 2 : 1;
-        // dQ(tile) = dS K       (contraction over the 128 keys); terms hi*hi, lo*hi, hi*lo
-        uint32_t acc = 0;
+        // dQ(tile) += dS K      (contraction over the 128 keys); terms hi*hi, lo*hi, hi*lo
+        const uint32_t t_dq = t_dq0 + (uint32_t)(q0 >> 7) * 64u;
+        uint32_t acc = k0 > 0 ? 1u : 0u;
         for (int term = 0; term < p.terms; ++term) {
           const uint32_t sa = term == 1 ? s_dsl : s_ds, sb = term == 2 ? s_kl : s_kh;
 #pragma unroll
@@ -580,27 +695,14 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         }
         umma_commit(bar);
       }
+      // the tensor cores are busy for a few thousand cycles: put the next iteration's tile loads in flight now
+      if (q0 + 128 < L) issue_q_do_loads(k0, q0 + 128);
+      else if (k0 + 128 < L) issue_q_do_loads(k0 + 128, 0);
       mbar_wait(bar, phase);
       phase ^= 1u;
       tcgen05_fence_after();
-      // ---- dQ rows of this query tile (columns [32 half, +32)): first key tile stores, later ones accumulate ----
-      {
-        float g[32];
-        ld_row32(t_dq + lane_off + (uint32_t)(half * 32), g);
-        if (q_ok) {
-          float4* dst = reinterpret_cast<float4*>(p.dq + ((int64_t)b * L + q) * p.dq_pitch + h * p.hd + half * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (half * 32 + 4 * j >= p.hd) continue;
-            float4 o = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-            if (k0 > 0) {
-              const float4 old = dst[j];
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            dst[j] = o;
-          }
-        }
-      }
+      ATTN_PROF(4 + ((k0 >> 7) * 2 + (q0 >> 7)) * 8);
+      ATTN_PROF(5 + ((k0 >> 7) * 2 + (q0 >> 7)) * 8);
       if (lo) {
         // dV += P_lo^T dO_hi through the same P buffer (all MMAs that read P_hi have completed)
 #pragma unroll 1
@@ -612,6 +714,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         fence_proxy_async();
         tcgen05_fence_before();
         __syncthreads();
+        ATTN_PROF(6 + ((k0 >> 7) * 2 + (q0 >> 7)) * 8);
         if (threadIdx.x == 0) {
           tcgen05_fence_after();
           const uint32_t idesc_t = make_idesc_rt(kHd, true, true);
@@ -626,30 +729,37 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         mbar_wait(bar, phase);
         phase ^= 1u;
         tcgen05_fence_after();
+        ATTN_PROF(7 + ((k0 >> 7) * 2 + (q0 >> 7)) * 8);
       }
       tcgen05_fence_before();
-      __syncthreads();  // Q / dO / P / dS tiles, s_red and the S / dP / dQ columns are reused
+      __syncthreads();  // Q / dO / P / dS tiles and the S / dP columns are reused
       tcgen05_fence_after();
     }
-    // ---- dK, dV rows of this key tile (thread = key, columns [32 half, +32)) ----
-    const int kk = k0 + row;
+    // ---- dK, dV rows of this key tile (thread = key, columns [32 half, +32)); staging tiles: the Q and dO tiles, dead
+    // until the next iteration's registers are converted into them ----
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      float* dstbase = which ? p.dv : p.dk;
-      const int64_t pitch = which ? p.dv_pitch : p.dk_pitch;
       float g[32];
       ld_row32((which ? t_dv : t_dk) + lane_off + (uint32_t)(half * 32), g);
-      if (kk < L) {
-        float4* dst = reinterpret_cast<float4*>(dstbase + ((int64_t)b * L + kk) * pitch + h * p.hd + half * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (half * 32 + 4 * j < p.hd) dst[j] = make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
-      }
+      store_tile_coalesced(which ? s_dh : s_qh, g, 1.f, row, half,
+                           (which ? p.dv : p.dk) + ((int64_t)b * L + k0) * (which ? p.dv_pitch : p.dk_pitch) + h * p.hd,
+                           which ? p.dv_pitch : p.dk_pitch, k_valid, p.hd);
     }
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
+    ATTN_PROF(40 + (k0 >> 7));
   }
+  // ---- dQ rows (thread = query, columns [32 half, +32)) ----
+  for (int q0 = 0; q0 < L; q0 += 128) {
+    float g[32];
+    ld_row32(t_dq0 + (uint32_t)(q0 >> 7) * 64u + lane_off + (uint32_t)(half * 32), g);
+    store_tile_coalesced(q0 ? s_dh : s_qh, g, 1.f, row, half, p.dq + ((int64_t)b * L + q0) * p.dq_pitch + h * p.hd, p.dq_pitch,
+                         (L - q0) < 128 ? (L - q0) : 128, p.hd);
+  }
+  ATTN_PROF(42);
+  tcgen05_fence_before();
+  __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
@@ -778,5 +888,11 @@ int atq_attention_bwd(int device, int B, int H, int L, int head_dim, const float
   ATQ_LAUNCH_CHECK();
   return ATQ_OK;
 }
+
+#ifdef ATQ_ATTN_PROF
+int atq_debug_attn_prof(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_attn_prof, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 }  // extern "C"

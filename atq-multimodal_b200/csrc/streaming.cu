@@ -1059,17 +1059,18 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
       for (int i = 0; i < kThreads / 32; ++i) amax = fmaxf(amax, s_m[i]);
       atomicMax(absmax_bits, __float_as_uint(amax));
+      __threadfence();
+      if (atomicAdd(absmax_bits + 3, 1u) == gridDim.x - 1) {  // last CTA: finish the slot and re-arm it (graph replays)
+        __threadfence();
+        float sc, inv;
+        pow2_scale_for(__uint_as_float(atomicExch(absmax_bits, 0u)), sc, inv);
+        float* slot = reinterpret_cast<float*>(absmax_bits);
+        slot[1] = sc;
+        slot[2] = inv;
+        absmax_bits[3] = 0u;
+      }
     }
   }
-}
-
-__global__ void scale_slot_finalize_kernel(float* slot, float bound_mul) {
-  unsigned int* bits = reinterpret_cast<unsigned int*>(slot);
-  float sc, inv;
-  pow2_scale_for(__uint_as_float(bits[0]) * bound_mul, sc, inv);
-  slot[1] = sc;
-  slot[2] = inv;
-  bits[0] = 0u;
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1693,10 +1694,6 @@ int atq_layernorm_fwd(int device, const float* x, const float* gamma, const floa
   layernorm_fwd_kernel<<<layernorm_grid(device, rows), kThreads, 0, stream>>>(x, gamma, beta, rows, (int)cols, eps, y, mean_out, rstd_out,
                                                                               reinterpret_cast<unsigned int*>(out_scale_slot));
   ATQ_LAUNCH_CHECK();
-  if (out_scale_slot != nullptr) {
-    scale_slot_finalize_kernel<<<1, 1, 0, stream>>>(out_scale_slot, 1.f);
-    ATQ_LAUNCH_CHECK();
-  }
   return ATQ_OK;
 }
 
