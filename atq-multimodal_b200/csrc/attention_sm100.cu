@@ -67,6 +67,13 @@ __device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
   return d;
 }
+// tile loads: plain global loads that bypass L1 (every byte is used once per CTA; the read-only texture path is slower
+// for this access pattern).  Not volatile: the compiler keeps all loads of a tile in flight together.
+__device__ __forceinline__ float4 ld_tile4(const float4* p) {
+  float4 v;
+  asm("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float bf16lo_f(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16hi_f(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -104,8 +111,8 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_
     for (int i = 0; i < PASSES; ++i) {
       const int r = r0 + i * kRowsPerPass;
       const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * pitch) + c;
-      a[i] = (r < rows_valid && va) ? __ldg(p) : zero;
-      b[i] = (r < rows_valid && vb) ? __ldg(p + 8) : zero;
+      a[i] = (r < rows_valid && va) ? ld_tile4(p) : zero;
+      b[i] = (r < rows_valid && vb) ? ld_tile4(p + 8) : zero;
     }
 #ifdef ATQ_ATTN_PROF
     if (PASSES == 8) {  // when did the last load land?
@@ -138,10 +145,10 @@ __device__ __forceinline__ void stage_two_tiles(const float* __restrict__ src0, 
     const int r = r0 + i * 32;
     const float4* p0 = reinterpret_cast<const float4*>(src0 + (int64_t)r * pitch0) + c;
     const float4* p1 = reinterpret_cast<const float4*>(src1 + (int64_t)r * pitch1) + c;
-    a0[i] = (r < rows_valid && va) ? __ldg(p0) : zero;
-    b0[i] = (r < rows_valid && vb) ? __ldg(p0 + 8) : zero;
-    a1[i] = (r < rows_valid && va) ? __ldg(p1) : zero;
-    b1[i] = (r < rows_valid && vb) ? __ldg(p1 + 8) : zero;
+    a0[i] = (r < rows_valid && va) ? ld_tile4(p0) : zero;
+    b0[i] = (r < rows_valid && vb) ? ld_tile4(p0 + 8) : zero;
+    a1[i] = (r < rows_valid && va) ? ld_tile4(p1) : zero;
+    b1[i] = (r < rows_valid && vb) ? ld_tile4(p1 + 8) : zero;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -170,14 +177,14 @@ __device__ __forceinline__ void load_q_do(QdoRegs& R, const float* __restrict__ 
     const bool ok = r < rows_valid;
     const float4* p0 = reinterpret_cast<const float4*>(qg + (int64_t)r * q_pitch) + c;
     const float4* p1 = reinterpret_cast<const float4*>(dg + (int64_t)r * do_pitch) + c;
-    R.a0[i] = (ok && va) ? __ldg(p0) : zero;
-    R.b0[i] = (ok && vb) ? __ldg(p0 + 8) : zero;
-    R.a1[i] = (ok && va) ? __ldg(p1) : zero;
-    R.b1[i] = (ok && vb) ? __ldg(p1 + 8) : zero;
+    R.a0[i] = (ok && va) ? ld_tile4(p0) : zero;
+    R.b0[i] = (ok && vb) ? ld_tile4(p0 + 8) : zero;
+    R.a1[i] = (ok && va) ? ld_tile4(p1) : zero;
+    R.b1[i] = (ok && vb) ? ld_tile4(p1 + 8) : zero;
     if (with_o) {
       const float4* p2 = reinterpret_cast<const float4*>(og + (int64_t)r * o_pitch) + c;
-      R.oa[i] = (ok && va) ? __ldg(p2) : zero;
-      R.ob[i] = (ok && vb) ? __ldg(p2 + 8) : zero;
+      R.oa[i] = (ok && va) ? ld_tile4(p2) : zero;
+      R.ob[i] = (ok && vb) ? ld_tile4(p2 + 8) : zero;
     }
   }
 }
@@ -316,6 +323,23 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(smem_u32(&s_tmem));
+  // the Q tile travels through registers: the loads of the next query tile are issued while the tensor cores and the
+  // softmax work on the current one
+  float4 qa[4], qb[4];
+  auto issue_q_loads = [&](int q0n) {
+    const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
+    const bool va = 4 * c < p.hd, vb = 32 + 4 * c < p.hd;
+    const int valid = (L - q0n) < 128 ? (L - q0n) : 128;
+    const float* qg = p.q + ((int64_t)b * L + q0n) * p.q_pitch + h * p.hd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + i * 32;
+      const float4* src = reinterpret_cast<const float4*>(qg + (int64_t)r * p.q_pitch) + c;
+      qa[i] = (r < valid && va) ? ld_tile4(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      qb[i] = (r < valid && vb) ? ld_tile4(src + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  issue_q_loads(0);
   build_valid_bits(p, b, s_valid);
   const float* kg = p.k + (int64_t)b * L * p.k_pitch + h * p.hd;
   const float* vg = p.v + (int64_t)b * L * p.v_pitch + h * p.hd;
@@ -345,23 +369,6 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
   uint32_t phase = 0;
 
-  // the Q tile travels through registers: the loads of the next query tile are issued while the tensor cores and the
-  // softmax work on the current one
-  float4 qa[4], qb[4];
-  auto issue_q_loads = [&](int q0n) {
-    const int c = threadIdx.x & 7, r0 = threadIdx.x >> 3;
-    const bool va = 4 * c < p.hd, vb = 32 + 4 * c < p.hd;
-    const int valid = (L - q0n) < 128 ? (L - q0n) : 128;
-    const float* qg = p.q + ((int64_t)b * L + q0n) * p.q_pitch + h * p.hd;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + i * 32;
-      const float4* src = reinterpret_cast<const float4*>(qg + (int64_t)r * p.q_pitch) + c;
-      qa[i] = (r < valid && va) ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-      qb[i] = (r < valid && vb) ? __ldg(src + 8) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  issue_q_loads(0);
   for (int q0 = 0; q0 < L; q0 += 128) {
     const int q_valid = (L - q0) < 128 ? (L - q0) : 128;
 #pragma unroll

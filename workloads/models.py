@@ -87,7 +87,7 @@ class TernaryAttention(nn.Module):
                 and self._core_ok(self.embed_dim, self.num_heads, q.size(1))):
             # own tcgen05 kernels: q/k/v stay in the [B, L, E] layout the projections wrote
             out = self._core(q, k, v, self.num_heads, key_padding_mask, self.attention_scale, self.dropout.p, self.training)
-            return self.out_proj(out) + 0.1 * query
+            return torch.add(self.out_proj(out), query, alpha=0.1)  # one pass instead of mul + add
         q = q.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
         k = k.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
         v = v.view(b, -1, self.num_heads, self.head_dim).transpose(1, 2)
@@ -99,13 +99,13 @@ class TernaryAttention(nn.Module):
             out = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask, scale=self.attention_scale,
                                                  dropout_p=self.dropout.p if self.training else 0.0)
             out = out.transpose(1, 2).reshape(b, -1, self.embed_dim)
-            return self.out_proj(out) + 0.1 * query
+            return torch.add(self.out_proj(out), query, alpha=0.1)  # one pass instead of mul + add
         scores = torch.matmul(q, k.transpose(-2, -1)) * self.attention_scale
         if key_padding_mask is not None:
             scores = scores.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
         probs = self.dropout(F.softmax(scores, dim=-1))
         out = torch.matmul(probs, v).transpose(1, 2).contiguous().view(b, -1, self.embed_dim)
-        return self.out_proj(out) + 0.1 * query
+        return torch.add(self.out_proj(out), query, alpha=0.1)  # one pass instead of mul + add
 
 
 class TernaryBlock(nn.Module):
