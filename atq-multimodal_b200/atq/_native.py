@@ -87,6 +87,7 @@ _SIGS = {
     "atq_colsum_f32": (c_int, [c_int, _P, c_int64, c_int64, c_int64, _P, _P, c_size_t, _P]),
     "atq_gelu_dropout_split": (c_int, [c_int, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, _P]),
     "atq_gelu_dropout_bwd_split_colsum": (c_int, [c_int, _P, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, _P, c_size_t, _P, _P]),
+    "atq_set_fused_select": (None, [c_int]),
     "atq_layernorm_fwd": (c_int, [c_int, _P, _P, _P, c_int64, c_int64, c_float, _P, _P, _P, _P, _P]),
     "atq_workspace_bytes_layernorm_bwd": (c_size_t, [c_int64]),
     "atq_layernorm_bwd": (c_int, [c_int, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, c_size_t, _P]),

@@ -225,6 +225,136 @@ __global__ void __launch_bounds__(kSelThreads) select_pass_kernel(SelectBatch b)
   if (threadIdx.x == 0) st->blocks_done = 0u;
 }
 
+// ---- fused plain select: the three digit passes in ONE cooperative launch -----------------------
+// The CTAs of a layer (blockIdx.y) meet at a layer-level barrier after each pass: the last CTA to flush its histogram
+// fixes the next digit and releases the others (a cooperative launch guarantees that all of them are resident).  The
+// second and third pass re-read the layer while it is still in L2 (layers up to ~64 MiB), instead of three launches that
+// each start cold.  State (histogram, ticket, release flag) is zeroed by a memset node in front of the kernel.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int PASS>
+__device__ __forceinline__ void fused_scan(uint32_t* sh, const float* __restrict__ x, long long n, uint32_t prefix) {
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+  long long head = (long long)(((16u - (unsigned)(addr & 15u)) & 15u) >> 2);
+  if (head > n) head = n;
+  const long long n4 = (n - head) >> 2;
+  const float* xb = x + head;
+  const long long stride = (long long)gridDim.x * kSelThreads;
+  const long long tid = (long long)blockIdx.x * kSelThreads + threadIdx.x;
+  for (long long g0 = tid; g0 < n4; g0 += stride * 4) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long g = g0 + j * stride;
+      if (g < n4) v[j] = __ldg(reinterpret_cast<const float4*>(xb + 4 * g));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long g = g0 + j * stride;
+      if (g < n4) {
+        hist_one<PASS>(sh, v[j].x, prefix);
+        hist_one<PASS>(sh, v[j].y, prefix);
+        hist_one<PASS>(sh, v[j].z, prefix);
+        hist_one<PASS>(sh, v[j].w, prefix);
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = threadIdx.x; i < head; i += kSelThreads) hist_one<PASS>(sh, x[i], prefix);
+    for (long long i = head + n4 * 4 + threadIdx.x; i < n; i += kSelThreads) hist_one<PASS>(sh, x[i], prefix);
+  }
+}
+
+// one pass: histogram, flush, layer barrier; returns the prefix with this pass's digit fixed (all threads)
+template <int PASS>
+__device__ __forceinline__ uint32_t fused_pass(const SelectBatch& b, int layer, SelectState* st, uint32_t prefix, uint32_t* sh,
+                                               unsigned long long* s_warp_tot, int* s_flag, uint32_t* s_prefix) {
+  constexpr int NB = (PASS == 0) ? kBins0 : kBins12;
+  constexpr int SHIFT = (PASS == 0) ? 20 : (PASS == 1 ? 10 : 0);
+  constexpr int PER_T = NB / kSelThreads;
+  for (int i = threadIdx.x; i < NB; i += kSelThreads) sh[i] = 0u;
+  __syncthreads();
+  fused_scan<PASS>(sh, b.x[layer], b.n[layer], prefix);
+  __syncthreads();
+  for (int i = threadIdx.x; i < NB; i += kSelThreads) {
+    const uint32_t c = sh[i];
+    if (c) atomicAdd(&st->hist[i], (unsigned long long)c);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) *s_flag = atomicAdd(&st->blocks_done, 1u) == (unsigned)(PASS + 1) * gridDim.x - 1u;
+  __syncthreads();
+  if (*s_flag) {
+    __threadfence();
+    unsigned long long c[PER_T], tsum = 0ull;
+#pragma unroll
+    for (int j = 0; j < PER_T; ++j) {
+      c[j] = __ldcg(&st->hist[threadIdx.x * PER_T + j]);
+      st->hist[threadIdx.x * PER_T + j] = 0ull;  // re-arm for the next pass
+      tsum += c[j];
+    }
+    unsigned long long incl = tsum;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp_tot[wid] = incl;
+    __syncthreads();
+    unsigned long long base = 0ull;
+    for (int i = 0; i < wid; ++i) base += s_warp_tot[i];
+    const unsigned long long excl = base + incl - tsum;
+    const unsigned long long k = PASS == 0 ? (unsigned long long)b.k[layer] : __ldcg(&st->k_rem);
+    if (excl <= k && k < excl + tsum) {
+      unsigned long long cum = excl;
+#pragma unroll
+      for (int j = 0; j < PER_T; ++j) {
+        if (k < cum + c[j]) {
+          const uint32_t np = prefix | ((uint32_t)(threadIdx.x * PER_T + j) << SHIFT);
+          st->prefix = np;
+          st->k_rem = k - cum;
+          *s_prefix = np;
+          if constexpr (PASS == 2) *b.thr_out[layer] = __uint_as_float(np);
+          break;
+        }
+        cum += c[j];
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (PASS < 2 && threadIdx.x == 0) st_release_u32(&st->pad[0], (unsigned)(PASS + 1));
+  } else if (PASS < 2) {
+    if (threadIdx.x == 0) {
+      while (ld_acquire_u32(&st->pad[0]) < (unsigned)(PASS + 1)) __nanosleep(64);
+      *s_prefix = __ldcg(&st->prefix);
+    }
+    __syncthreads();
+  }
+  return PASS < 2 ? *s_prefix : 0u;
+}
+
+__global__ void __launch_bounds__(kSelThreads) select_fused_kernel(SelectBatch b) {
+  __shared__ uint32_t sh[kBins0];
+  __shared__ unsigned long long s_warp_tot[kSelThreads / 32];
+  __shared__ int s_flag;
+  __shared__ uint32_t s_prefix;
+  const int layer = blockIdx.y;
+  SelectState* st = b.states + layer;
+  uint32_t prefix = fused_pass<0>(b, layer, st, 0u, sh, s_warp_tot, &s_flag, &s_prefix);
+  __syncthreads();
+  prefix = fused_pass<1>(b, layer, st, prefix, sh, s_warp_tot, &s_flag, &s_prefix);
+  __syncthreads();
+  fused_pass<2>(b, layer, st, prefix, sh, s_warp_tot, &s_flag, &s_prefix);
+}
+
 // ---- sampling front-end (batched: blockIdx.y = layer) -------------------------------------------
 constexpr int kPivots = 512;
 constexpr int kPivotsPerCta = 8;
@@ -460,6 +590,8 @@ static inline unsigned long long cand_capacity(int64_t n) {
 
 using namespace atq;
 
+static bool g_fused_select = true;  // atq_set_fused_select (measurement switch)
+
 static int check_launch(const char* what, int nlaunches) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -481,8 +613,33 @@ static int select_plain_batch(int device, int cnt, const float* const* xs, const
     if (ns[i] > max_n) max_n = ns[i];
   }
   b.states = states;
-  // CTAs per layer: 16 elements per thread per trip, capped so that the launch is ~8 CTAs per SM
   int64_t need = (max_n + (int64_t)kSelThreads * 16 - 1) / ((int64_t)kSelThreads * 16);
+  // one cooperative launch (all CTAs resident, layer-level barriers between the digit passes) when the device allows it
+  static int coop_cap[64] = {0};  // resident CTAs of select_fused_kernel per device; -1 = no cooperative launch
+  int& cc = coop_cap[device & 63];
+  if (cc == 0) {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, select_fused_kernel, kSelThreads, 0) == cudaSuccess && per_sm > 0)
+      cc = per_sm * sm_count(device);
+    else
+      cc = -1;
+  }
+  if (cc >= cnt && g_fused_select) {
+    int64_t cap = cc / cnt;
+    int gx = (int)(need < cap ? need : cap);
+    if (gx < 1) gx = 1;
+    if (cudaMemsetAsync(states, 0, sizeof(SelectState) * (size_t)cnt, stream) != cudaSuccess) return check_launch("select", 0);
+    void* args[1] = {&b};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(select_fused_kernel), dim3((unsigned)gx, (unsigned)cnt),
+                                                dim3(kSelThreads), args, 0, stream);
+    if (e != cudaSuccess) {
+      set_error("select: cooperative launch failed: %s", cudaGetErrorString(e));
+      return ATQ_ECUDA;
+    }
+    return check_launch("select", 1);
+  }
+  // CTAs per layer: 16 elements per thread per trip, capped so that the launch is ~8 CTAs per SM
   int64_t cap = ((int64_t)sm_count(device) * 8 + cnt - 1) / cnt;
   if (cap < 1) cap = 1;
   int gx = (int)(need < cap ? need : cap);
@@ -580,6 +737,8 @@ __global__ void set_caps_kernel(SampleState* ss, const unsigned long long c0, co
 }
 
 extern "C" {
+
+void atq_set_fused_select(int enabled) { g_fused_select = enabled != 0; }
 
 size_t atq_workspace_bytes_adaptive_threshold_batched(int count, const int64_t* ns) { return plan_ws(count, ns).total; }
 size_t atq_workspace_bytes_select_kth_abs(int64_t n) { return plan_ws(1, &n).total; }

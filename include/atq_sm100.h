@@ -60,6 +60,10 @@ size_t atq_workspace_bytes_select_kth_abs(int64_t n);
 int atq_select_kth_abs(int device, const float* x, int64_t n, int64_t k, float* thr_out,
                        void* ws, size_t ws_bytes, atq_stream_t stream);
 
+/* Measurement switch: 1 (default) = the three digit passes of the exact select run in ONE cooperative launch with
+ * layer-level barriers (re-reading the layer from L2); 0 = one launch per pass. */
+void atq_set_fused_select(int enabled);
+
 /* The whole threshold stage with the reference's three branches, keyed by
  * k = int(sparsity_target * n) computed by the caller in double precision:
  *   0 < k < n : k-th order statistic           (:31-32)

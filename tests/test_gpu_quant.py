@@ -277,3 +277,37 @@ def test_batched_codec_matches_per_layer_and_oracle():
     badp[0][123] = 0xFF
     _, flag = eng.unpack2_batched(badp, [w.numel() for w in ws])
     assert int(flag) == 1
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+def test_select_fused_and_per_pass_paths_agree_with_sort(fused):
+    """The exact select runs its three digit passes in one cooperative launch (default) or as one launch per pass
+    (atq_set_fused_select(0)); both must return sorted(|x|)[k] bit for bit -- single layers (ragged sizes, unaligned
+    start, ties, constants, first and last rank) and a batch of layers of mixed sizes, twice in a row (state re-armed)."""
+    import atq._native as nv
+    nv.lib.atq_set_fused_select(fused)
+    try:
+        g = torch.Generator().manual_seed(17)
+        cases = [torch.randn(n, generator=g) for n in (1, 2, 5, 1001, 65537, (1 << 20) + 3, 5_000_011)]
+        cases.append(torch.randint(-3, 4, (300_001,), generator=g).float())     # heavy ties
+        cases.append(torch.full((70_000,), -0.375))                              # constant
+        big = torch.randn((1 << 20) + 9, generator=g)
+        cases.append(big[1:])                                                    # 4-byte aligned, not 16
+        for x in cases:
+            xg = x.to(DEV)
+            if x.data_ptr() != x.untyped_storage().data_ptr():                  # keep the misalignment on the device
+                xg = big.to(DEV)[1:]
+            srt = torch.sort(xg.abs()).values
+            n = xg.numel()
+            for k in sorted({0, n // 3, n // 2, n - 1}):
+                for _ in range(2):
+                    got = eng.select_kth_abs(xg, k)
+                    assert got.item() == srt[k].item(), (fused, n, k)
+        ws = [torch.randn(s, generator=g).to(DEV) for s in ((192, 192), (1000, 1003), (7,), (2048, 1024), (33, 65))]
+        ss = [0.3, 0.05, 0.5, 0.1333, 0.999]
+        for _ in range(2):
+            thr = eng.adaptive_threshold_batched(ws, ss)
+            for t, w, s in zip(thr, ws, ss):
+                assert t.item() == np.float32(O.adaptive_threshold(w.cpu().numpy(), s)), (fused, tuple(w.shape), s)
+    finally:
+        nv.lib.atq_set_fused_select(1)
