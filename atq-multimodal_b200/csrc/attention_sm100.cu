@@ -365,6 +365,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const unsigned long long seed = p.seed != nullptr ? *p.seed : 0ull;
   const float c2 = p.scale * 1.4426950408889634f;
+  const float log2_inv_keep = p.drop_thresh != 0u ? __log2f(p.inv_keep) : 0.f;
+  const float keep = p.drop_thresh != 0u ? 1.f / p.inv_keep : 1.f;
+  const uint32_t thr_hi = p.drop_thresh << 16;
   const int nch = NK / 32;
   const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
   uint32_t phase = 0;
@@ -420,26 +423,34 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
     if (m == -INFINITY) m = 0.f;  // every key masked: probabilities are all zero below
     __syncthreads();              // s_red is reused for the row sums
     ATTN_PROF(4 + (q0 >> 7) * 8);
-    const float mc = m * c2;
+    // dropout keeps p / (1 - rate): the factor rides in the exponent, and the row sum (taken before the mask) is scaled back
+    const float mc = m * c2 - log2_inv_keep;
     const uint32_t row_key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * L + q0 + row));
     float sum = 0.f;
     for (int ch = ch_lo; ch < ch_hi; ++ch) {
       float s[32];
       ld_row32(t_row + (uint32_t)(ch * 32), s);
       const uint32_t vb = s_valid[ch];
+      if (vb == 0xffffffffu) {  // warp-uniform: every key of this chunk is valid
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float pj = ex2_approx(fmaf(s[j], c2, -mc));
-        if (vb != 0xffffffffu) pj = ((vb >> j) & 1u) ? pj : 0.f;
-        sum += pj;
-        s[j] = pj;
+        for (int j = 0; j < 32; ++j) {
+          s[j] = ex2_approx(fmaf(s[j], c2, -mc));
+          sum += s[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pj = ((vb >> j) & 1u) ? ex2_approx(fmaf(s[j], c2, -mc)) : 0.f;
+          sum += pj;
+          s[j] = pj;
+        }
       }
       if (p.drop_thresh != 0u) {
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           const uint32_t hsh = drop_hash_pair(row_key, (uint32_t)(ch * 16 + (j >> 1)));
-          s[j] = (hsh & 0xFFFFu) >= p.drop_thresh ? s[j] * p.inv_keep : 0.f;
-          s[j + 1] = (hsh >> 16) >= p.drop_thresh ? s[j + 1] * p.inv_keep : 0.f;
+          s[j] = (hsh << 16) >= thr_hi ? s[j] : 0.f;      // low 16 bits >= threshold
+          s[j + 1] = hsh >= thr_hi ? s[j + 1] : 0.f;      // high 16 bits >= threshold
         }
       }
       if (lo) {
@@ -472,7 +483,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_fwd_kernel(const Att
       }
       umma_commit(bar);
     }
-    sum = s_red[0][row] + s_red[1][row];
+    sum = (s_red[0][row] + s_red[1][row]) * keep;
     mbar_wait(bar, phase);
     phase ^= 1u;
     tcgen05_fence_after();
@@ -564,6 +575,9 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
   const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
   const unsigned long long seed = p.seed != nullptr ? *p.seed : 0ull;
   const float c2 = p.scale * 1.4426950408889634f;
+  const float log2_inv_keep = p.drop_thresh != 0u ? __log2f(p.inv_keep) : 0.f;
+  const float keep = p.drop_thresh != 0u ? 1.f / p.inv_keep : 1.f;
+  const uint32_t thr_hi = p.drop_thresh << 16;
   uint32_t phase = 0;
 
   QdoRegs R;
@@ -614,8 +628,8 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         }
         umma_commit(bar);
       }
-      const float delta = s_delta[q0 >> 7][row];
-      const float lse2 = lse_q * 1.4426950408889634f;
+      const float delta_keep = s_delta[q0 >> 7][row] * keep;
+      const float lse2 = lse_q * 1.4426950408889634f - log2_inv_keep;
       const uint32_t row_key = drop_row_key((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)(bh * L + q));
       mbar_wait(bar, phase);
       phase ^= 1u;
@@ -629,26 +643,28 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
         ld_row32(t_s + lane_off + (uint32_t)(ch * 32), s);
         ld_row32(t_dp + lane_off + (uint32_t)(ch * 32), dp);
         const uint32_t vb = q_ok ? s_valid[(k0 >> 5) + ch] : 0u;
+        // s <- p / (1 - rate) (the dropout factor rides in the exponent), dp <- p (dP_kept - delta) / scale-free dS: the
+        // softmax scale is applied to the dQ / dK tiles when they are stored
+        if (vb == 0xffffffffu) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float pj = ex2_approx(fmaf(s[j], c2, -lse2));
-          if (vb != 0xffffffffu) pj = ((vb >> j) & 1u) ? pj : 0.f;
-          s[j] = pj;
+          for (int j = 0; j < 32; ++j) s[j] = ex2_approx(fmaf(s[j], c2, -lse2));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s[j] = ((vb >> j) & 1u) ? ex2_approx(fmaf(s[j], c2, -lse2)) : 0.f;
         }
         if (p.drop_thresh != 0u) {
 #pragma unroll
           for (int j = 0; j < 32; j += 2) {
             const uint32_t hsh = drop_hash_pair(row_key, (uint32_t)((k0 >> 1) + ch * 16 + (j >> 1)));
-            const float k0f = (hsh & 0xFFFFu) >= p.drop_thresh ? p.inv_keep : 0.f;
-            const float k1f = (hsh >> 16) >= p.drop_thresh ? p.inv_keep : 0.f;
-            dp[j] = s[j] * (dp[j] * k0f - delta) * p.scale;          // dS uses the un-dropped probability
-            dp[j + 1] = s[j + 1] * (dp[j + 1] * k1f - delta) * p.scale;
-            s[j] *= k0f;                                              // dropped probabilities (dV operand)
-            s[j + 1] *= k1f;
+            const bool k0b = (hsh << 16) >= thr_hi, k1b = hsh >= thr_hi;
+            dp[j] = s[j] * ((k0b ? dp[j] : 0.f) - delta_keep);         // dS uses the un-dropped probability
+            dp[j + 1] = s[j + 1] * ((k1b ? dp[j + 1] : 0.f) - delta_keep);
+            s[j] = k0b ? s[j] : 0.f;                                    // dropped probabilities (dV operand)
+            s[j + 1] = k1b ? s[j + 1] : 0.f;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dp[j] = s[j] * (dp[j] - delta) * p.scale;
+          for (int j = 0; j < 32; ++j) dp[j] = s[j] * (dp[j] - delta_keep);
         }
         if (lo) {
           store_row32_bf16<true>(s_p, row, ch, s);
@@ -748,7 +764,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
     for (int which = 0; which < 2; ++which) {
       float g[32];
       ld_row32((which ? t_dv : t_dk) + lane_off + (uint32_t)(half * 32), g);
-      store_tile_coalesced(which ? s_dh : s_qh, g, 1.f, row, half,
+      store_tile_coalesced(which ? s_dh : s_qh, g, which ? 1.f : p.scale, row, half,
                            (which ? p.dv : p.dk) + ((int64_t)b * L + k0) * (which ? p.dv_pitch : p.dk_pitch) + h * p.hd,
                            which ? p.dv_pitch : p.dk_pitch, k_valid, p.hd);
     }
@@ -761,7 +777,7 @@ __global__ void __launch_bounds__(kAttThreads, 1) attention_bwd_kernel(const Att
   for (int q0 = 0; q0 < L; q0 += 128) {
     float g[32];
     ld_row32(t_dq0 + (uint32_t)(q0 >> 7) * 64u + lane_off + (uint32_t)(half * 32), g);
-    store_tile_coalesced(q0 ? s_dh : s_qh, g, 1.f, row, half, p.dq + ((int64_t)b * L + q0) * p.dq_pitch + h * p.hd, p.dq_pitch,
+    store_tile_coalesced(q0 ? s_dh : s_qh, g, p.scale, row, half, p.dq + ((int64_t)b * L + q0) * p.dq_pitch + h * p.hd, p.dq_pitch,
                          (L - q0) < 128 ? (L - q0) : 128, p.hd);
   }
   ATTN_PROF(42);
