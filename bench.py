@@ -338,11 +338,20 @@ def attention_rooflines(device, peaks, flush):
             q.grad = k.grad = v.grad = None
             o.backward(dout, retain_graph=True)
         ms_b = _event_time(bwd, 4, flush)
-        for name, ms, fl in (("attention_fwd_kernel", ms_f, 4.0), ("attention_bwd_kernel", ms_b, 10.0)):
+        # algorithmic bytes: forward reads q, k, v and writes out; backward reads q, k, v, out, dout and writes dq, dk, dv
+        # (fp32 [B, L, E] tensors).  At L = 197, head_dim 64 the HBM time (1.24 GB / 2.48 GB) is above the tensor time of
+        # the useful flops, so the second roofline ("hbm") is the binding one; both are reported.
+        tensor_bytes = 4.0 * b_ * l_ * h_ * 64
+        for name, ms, fl, nten, key in (("attention_fwd_kernel", ms_f, 4.0, 4, "attention fwd parity"),
+                                        ("attention_bwd_kernel", ms_b, 10.0, 8, "attention bwd parity")):
             ach = fl * l_ * l_ * 64 * b_ * h_ / (ms * 1e-3) / 1e12
+            gbs = nten * tensor_bytes / (ms * 1e-3) / 1e9
             out.append({"kernel": f"{name} {mode}", "workload": f"config4 attention core {b_}x{h_}x{l_}x64, dropout 0.1",
                         "bound": "tensor", "achieved": round(ach, 1), "peak": tf, "unit": "TFLOP/s", "frac": round(ach / tf, 4),
-                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4), "traffic": None})
+                        "peak_kind": f"bf16 burst {src}", "ms": round(ms, 4),
+                        "hbm": {"achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 4),
+                                "alg_bytes": nten * tensor_bytes},
+                        "traffic": NCU_TRAFFIC.get(key) if mode == "parity" else None})
         del o
     atq.set_gemm_mode(prev_mode)
     return out

@@ -62,5 +62,23 @@ if which in ("all", "loss"):
     for _ in range(reps):
         img.grad = txt.grad = None
         crit(img, txt).backward()
+if which == "r02b":
+    # final round-2 capture: parity GEMMs (CTA pairs, wide tiles), attention core, LayerNorm, fused select -- one pass each
+    atq.set_gemm_mode("parity")
+    tl = atq.TernaryLinear(K, M).to(dev)
+    rpb = atq.ResidualPrecisionBoostLinear(K, M, 0.05, True, 0.3).to(dev)
+    for mod in (tl, rpb):
+        xi = x.clone().requires_grad_(True)
+        mod(xi).backward(gy)
+    from atq.attention import attention_core
+    B, H, L, D = 512, 12, 197, 64
+    q, k, v = (torch.randn(B, L, H * D, device=dev, generator=g).requires_grad_(True) for _ in range(3))
+    do = torch.randn(B, L, H * D, device=dev, generator=g)
+    attention_core(q, k, v, H, None, None, 0.1, True).backward(do)
+    xl = torch.randn(B * L, 768, device=dev, generator=g).requires_grad_(True)
+    wl = torch.ones(768, device=dev, requires_grad=True)
+    bl = torch.zeros(768, device=dev, requires_grad=True)
+    atq.layer_norm(xl, wl, bl).backward(torch.randn(B * L, 768, device=dev, generator=g))
+    thr = eng.adaptive_threshold(w, 0.3)          # fused cooperative select (16 M)
 torch.cuda.synchronize()
 print("done")
