@@ -19,9 +19,11 @@ cfg = T.FLICKR8K_SHAPE
 dev = torch.device("cuda:0")
 model, _, manager = T.build_retrieval(atq, cfg)
 model.to(dev).train()
+model.image_encoder.base_model.to(memory_format=torch.channels_last)  # as bench.py does (caller-side layout of the fp32 trunk)
 GradualQuantizationScheduler(model, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs).step(cfg.epoch)
 opt = T.make_optimizer(model, cfg, fused=True)
 batches = [tuple(t.to(dev) for t in b) for b in T.synthetic_batches(cfg, 2, seed=42)]
+batches = [(b[0].contiguous(memory_format=torch.channels_last),) + b[1:] for b in batches]
 for i in range(3):
     T.retrieval_step(model, manager, opt, batches[i % 2], prepare=atq.prepare_quantization)
 torch.cuda.synchronize()
