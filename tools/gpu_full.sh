@@ -11,6 +11,6 @@ d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-
 print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, 'e2e', d['e2e']['value'])
 print('cpu', d['cpu_baseline']); print('vit', {k:d['configs']['vitb16'][k] for k in ('value','ms_per_step')}); print('dropin', d.get('dropin'))
 print(d['roofline'])
-for r in d['rooflines']: print(r['kernel'][:60], '|', r['workload'][:60], '|', r.get('ms'), r['frac'])
+for r in d['rooflines']: print(r['kernel'][:60], '|', r['workload'][:60], '|', r.get('ms'), r.get('frac'))
 print(d.get('summary'))
 PY
