@@ -105,7 +105,9 @@ class TernaryAttention(nn.Module):
             scores = scores.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
         probs = self.dropout(F.softmax(scores, dim=-1))
         out = torch.matmul(probs, v).transpose(1, 2).contiguous().view(b, -1, self.embed_dim)
-        return torch.add(self.out_proj(out), query, alpha=0.1)  # one pass instead of mul + add
+        # the reference's own expression (mul, then add: two roundings) - this branch is the one the CPU test pins
+        # bit-for-bit against the reference's layer; torch.add(alpha=) above is a single fused pass (one rounding)
+        return self.out_proj(out) + 0.1 * query
 
 
 class TernaryBlock(nn.Module):
