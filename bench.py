@@ -241,20 +241,33 @@ def cpu_baseline_subprocess(args, workload):
 # ---------------------------------------------------------------------------------------
 # kernel-level rooflines measured live (CUDA events, this process)
 # ---------------------------------------------------------------------------------------
+_LEAD_CYCLES = 3_000_000  # ~1.5 ms at 1.965 GHz
+
+
 def _event_time(fn, iters, flush=None):
+    """Median device time of fn() in ms.  Per iteration: L2 flush, then a device-side spin (`torch.cuda._sleep`, one
+    thread, no memory traffic) that the host uses to enqueue fn() completely - tensor allocation, ctypes pointer tables and
+    launch latency of a 60-layer batched call are ~0.3-0.5 ms of Python, more than several of the kernels measured here -
+    so the two events bracket the kernels back to back, i.e. launch durations, not host latency."""
     fn()
     torch.cuda.synchronize()
-    total = 0.0
+    times = []
     for _ in range(iters):
         if flush is not None:
             flush()
+        torch.cuda._sleep(_LEAD_CYCLES)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
         e.record()
         torch.cuda.synchronize()
-        total += s.elapsed_time(e)
-    return total / iters  # ms
+        times.append(s.elapsed_time(e))
+    times.sort()
+    return times[len(times) // 2]  # ms
+
+
+TIMING_NOTE = ("median of the iterations; CUDA events on the launching stream; L2 flushed before each; host launch latency "
+               "hidden behind a 1.5 ms device-side spin queued ahead of the start event")
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` captures (profiles/)
@@ -299,8 +312,8 @@ def gemm_rooflines(device, peaks, flush):
                     xi.grad = None
                     mod(xi).backward(gy)
 
-                ms_f = _event_time(fwd, 4, flush)
-                ms_fb = _event_time(fwdbwd, 4, flush)
+                ms_f = _event_time(fwd, 5, flush)
+                ms_fb = _event_time(fwdbwd, 5, flush)
                 n_gemm = 2 if ratio is None else 3
                 fl = 2.0 * N * size * size
                 key = f"{kind} {size} {mode}"
@@ -331,13 +344,13 @@ def attention_rooflines(device, peaks, flush):
     for mode in ("fast", "parity"):
         atq.set_gemm_mode(mode)
         with torch.no_grad():
-            ms_f = _event_time(lambda: A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed), 4, flush)
+            ms_f = _event_time(lambda: A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed), 5, flush)
         o = A.attention_core(q, k, v, h_, None, None, 0.1, True, seed=seed)
 
         def bwd():
             q.grad = k.grad = v.grad = None
             o.backward(dout, retain_graph=True)
-        ms_b = _event_time(bwd, 4, flush)
+        ms_b = _event_time(bwd, 5, flush)
         # algorithmic bytes: forward reads q, k, v and writes out; backward reads q, k, v, out, dout and writes dq, dk, dv
         # (fp32 [B, L, E] tensors).  At L = 197, head_dim 64 the HBM time (1.24 GB / 2.48 GB) is above the tensor time of
         # the useful flops, so the second roofline ("hbm") is the binding one; both are reported.
@@ -406,18 +419,18 @@ def streaming_rooflines(device, peaks, flush):
         return eng.ternarize_pack2_batched(ws, th)     # one launch for all layers
 
     packed = quantize_pack()
-    rec("threshold, batched over layers", wl, 4.0, total, _event_time(lambda: eng.adaptive_threshold_batched(ws, ss), 3, flush))
-    ms_qp = _event_time(quantize_pack, 3, flush)
+    rec("threshold, batched over layers", wl, 4.0, total, _event_time(lambda: eng.adaptive_threshold_batched(ws, ss), 5, flush))
+    ms_qp = _event_time(quantize_pack, 5, flush)
     rec("quantize+pack (threshold + ternarize -> 2-bit)", wl, 8.25, total, ms_qp, None,
         "two-read bound 8.25 B/elem (one read for the order statistic, one for ternarize); single-read bound 4.25 -> "
         f"{round(4.25 * total / (ms_qp * 1e-3) / 1e9 / hbm, 4)} of peak")
     numels = [t.numel() for t in ws]
     th = eng.adaptive_threshold_batched(ws, ss)
-    rec("ternarize -> 2-bit, batched over layers", wl, 4.25, total, _event_time(lambda: eng.ternarize_pack2_batched(ws, th), 3, flush))
-    rec("unpack 2-bit -> fp32", wl, 4.25, total, _event_time(lambda: eng.unpack2_batched(packed, numels), 3, flush))
+    rec("ternarize -> 2-bit, batched over layers", wl, 4.25, total, _event_time(lambda: eng.ternarize_pack2_batched(ws, th), 5, flush))
+    rec("unpack 2-bit -> fp32", wl, 4.25, total, _event_time(lambda: eng.unpack2_batched(packed, numels), 5, flush))
     tern, _ = eng.unpack2_batched(packed, numels)
     del ws
-    rec("pack fp32 ternary -> 2-bit", wl, 4.25, total, _event_time(lambda: eng.pack2_from_f32_batched(tern), 3, flush))
+    rec("pack fp32 ternary -> 2-bit", wl, 4.25, total, _event_time(lambda: eng.pack2_from_f32_batched(tern), 5, flush))
     out.append({"kernel": "quantize+pack throughput", "workload": wl, "gelem_per_s": round(total / ms_qp / 1e6, 1)})
     del tern, packed
     torch.cuda.empty_cache()
@@ -686,6 +699,7 @@ def run_ours(args, cfg):
             flush = ctx["flush"]
             rl = attention_rooflines(device, peaks, flush) + streaming_rooflines(device, peaks, flush) + gemm_rooflines(device, peaks, flush)
             line["rooflines"] = rl
+            line["rooflines_timing"] = TIMING_NOTE
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_subprocess(args, args.workload)
         if world == 1 and not args.no_dropin and cfg.image_tower == "resnet18":

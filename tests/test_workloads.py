@@ -175,3 +175,29 @@ def test_fused_attention_core_matches_explicit_sequence():
         finally:
             M.FUSED_ATTENTION_CORE = True
     assert torch.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-4)  # outputs reach ~1e2
+
+
+def test_schedule_fingerprint_tracks_every_baked_scalar():
+    """GraphedRetrievalStep re-captures when a host-side scalar baked into the capture moves (the reference changes
+    them between epochs: train_multimodal.py:403-413 LR scheduler, set_epoch; mixed_precision_atq.py:323-401)."""
+    cfg = T.RetrievalCfg(name="t", vocab=200, embed_dim=32, hidden_dim=64, image_size=32, batch=4)
+    model, crit, man = T.build_retrieval(M.oracle_layers(), cfg)
+    opt = T.make_optimizer(model, cfg)
+    f0 = T.schedule_fingerprint(model, man, opt)
+    assert f0 == T.schedule_fingerprint(model, man, opt)
+    opt.param_groups[0]["lr"] *= 0.5
+    f1 = T.schedule_fingerprint(model, man, opt)
+    assert f1 != f0
+    P.scheduler_step(model, cfg.epoch + 1, cfg.total_epochs, 0.3, 0.2, warmup_epochs=cfg.warmup_epochs)
+    f2 = T.schedule_fingerprint(model, man, opt)
+    assert f2 != f1
+    crit.set_epoch(cfg.epoch + 1, cfg.total_epochs)
+    f3 = T.schedule_fingerprint(model, man, opt)
+    assert f3 != f2
+    man.set_epoch(cfg.total_epochs - 1, cfg.total_epochs)
+    assert T.schedule_fingerprint(model, man, opt) != f3
+    # a learning rate held in a device tensor is read at replay time: not part of the fingerprint
+    opt.param_groups[0]["lr"] = torch.tensor(1e-4)
+    f4 = T.schedule_fingerprint(model, man, opt)
+    opt.param_groups[0]["lr"] = torch.tensor(2e-4)
+    assert T.schedule_fingerprint(model, man, opt) == f4

@@ -142,16 +142,50 @@ def classifier_step(model, optimizer, batch):
 
 # ---- CUDA-graph capture of the whole optimisation step ----------------------------------
 
+def schedule_fingerprint(model, manager, optimizer):
+    """Every host-side scalar a captured step bakes in (see GraphedRetrievalStep): a tuple that changes exactly when
+    a replay would train with a stale value.  ~30 us for config 2's 28 layers."""
+    items = []
+    for m in model.modules():
+        st = getattr(m, "sparsity_target", None)
+        if st is not None and not isinstance(st, torch.Tensor):
+            items.append(float(st))
+    for g in optimizer.param_groups:
+        for key in ("lr", "betas", "eps", "weight_decay"):
+            v = g.get(key)
+            if not isinstance(v, torch.Tensor):  # a device tensor is read by the kernel at replay time: nothing baked
+                items.append(v)
+    for obj in (manager, getattr(manager, "criterion", None)):
+        for key in ("epoch", "total_epochs", "curriculum_stage", "current_epoch", "temperature", "base_temperature",
+                    "lambda_reg", "hard_negative_weight", "hardest_mining_ratio", "temperature_schedule"):
+            if obj is not None and hasattr(obj, key):
+                items.append(getattr(obj, key))
+    try:
+        import atq
+        items.append(atq.get_gemm_mode())
+    except (ImportError, AttributeError):
+        pass
+    return tuple(items)
+
+
 class GraphedRetrievalStep:
     """Captures zero_grad + forward + loss + backward (+ gradient all-reduce) + AdamW into ONE CUDA
     graph.  The small-shape configs are launch-bound (~1000 kernels per step, most a few
     microseconds); the hot path was written without host synchronisation (thresholds, alpha and the
     validation flags stay on the device) precisely so that it can be captured.  Replays re-run the
-    per-layer quantization kernels on the live weights, exactly like the eager step."""
+    per-layer quantization kernels on the live weights, exactly like the eager step.
+
+    Host-side scalars are baked into a capture: every layer's k = int(sparsity_target * numel) and mode, the
+    optimizer's lr / betas / eps / weight decay, the loss temperature and curriculum stage, the GEMM mode.  The
+    reference changes them between epochs (GradualQuantizationScheduler.step, MixedPrecisionATQ, LR schedulers,
+    set_epoch), so `__call__` compares a fingerprint of those scalars with the one taken at capture and RE-CAPTURES when
+    it moved (`recaptures` counts them) - a replay never trains with a stale schedule."""
 
     def __init__(self, model, manager, optimizer, example_batch, gather=None, grad_sync=None, warmup=3, prepare=None):
-        self.model = model
+        self.model, self.manager, self.optimizer = model, manager, optimizer
+        self.gather, self.grad_sync, self.prepare = gather, grad_sync, prepare
         self.static_batch = tuple(t.clone() for t in example_batch)
+        self.recaptures = 0
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -160,20 +194,30 @@ class GraphedRetrievalStep:
                 retrieval_step(model, manager, optimizer, self.static_batch, gather, grad_sync, prepare)
         cur.wait_stream(side)
         torch.cuda.synchronize()
+        self._capture()
+
+    def _capture(self):
         self.graph = torch.cuda.CUDAGraph()
-        if grad_sync is None:
-            optimizer.zero_grad(set_to_none=True)
+        if self.grad_sync is None:
+            self.optimizer.zero_grad(set_to_none=True)
         try:
             import atq._native as nv
             k0 = nv.kernel_launch_count()
         except ImportError:
             nv, k0 = None, 0
+        self.fingerprint = schedule_fingerprint(self.model, self.manager, self.optimizer)
         with torch.cuda.graph(self.graph):
-            self.static_loss = retrieval_step(model, manager, optimizer, self.static_batch, gather, grad_sync, prepare)
+            self.static_loss = retrieval_step(self.model, self.manager, self.optimizer, self.static_batch, self.gather,
+                                              self.grad_sync, self.prepare)
         # kernels of libatq_sm100 recorded in the graph (each replay launches them again)
         self.own_kernels_per_replay = (nv.kernel_launch_count() - k0) if nv is not None else 0
 
     def __call__(self, batch):
+        if schedule_fingerprint(self.model, self.manager, self.optimizer) != self.fingerprint:
+            torch.cuda.synchronize()   # the old graph's replays must be finished before its memory pool is dropped
+            self.graph = None
+            self.recaptures += 1
+            self._capture()
         for dst, src in zip(self.static_batch, batch):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
