@@ -92,6 +92,7 @@ __device__ __forceinline__ void unpack16_to_bf16(uint32_t w, uint4& lo8, uint4& 
 // ------------------------------------------------------------------------------------------
 enum { EPI_LINEAR = 0, EPI_MASKED = 1 };
 static bool g_cta_pairs = true;   // atq_set_cta_pairs(): A/B switch for the cta_group::2 kernels
+static bool g_force_pairs = false;  // bit 3: pairs also below one wave of single-CTA tiles
 static bool g_wide_pairs = true;  // bit 1 of the same switch: 256-wide single-buffered pair tiles for long contractions
 
 struct GemmParams {
@@ -824,7 +825,13 @@ static int dispatch_layout(const atq_bf16_operand* a, const atq_bf16_operand* b,
   // double-buffered, so those kernels use 128-wide tiles; single-term GEMMs use 256-wide tiles when wide enough
   // CTA pairs (cta_group::2) once the output has at least one 256-row tile per pair-column: halves the B-operand
   // shared-memory reads per flop of the 128-wide dual-accumulator tiles
-  const bool pairs = g_cta_pairs && p.rows >= 256 && p.cols >= 128;
+  // ... and only when the problem fills the machine at least once with single-CTA tiles: below that the GEMM is bound by
+  // its fixed latency, and the cluster launch + the two cluster barriers of a pair cost more than the shared-memory
+  // bandwidth they save (CUPTI, 800 x 192 x 192, 3 terms: 9.2 us as pairs, 8.0 us as single CTAs; dX 8.7 vs 7.6 us)
+  int dev_p = 0;
+  cudaGetDevice(&dev_p);
+  const int64_t tiles128 = ((p.rows + BLOCK_M - 1) / BLOCK_M) * ((p.cols + 127) / 128) * (p.splits > 1 ? p.splits : 1);
+  const bool pairs = g_cta_pairs && p.rows >= 256 && p.cols >= 128 && (g_force_pairs || tiles128 >= sm_count(dev_p));
 #define ATQ_GO2(NA, NB, BN) return launch_cfg<NA, NB, BN, EPI, false, LAYOUT, BLOCK_K, true>(a, b, p, stream, grid_used)
   if (pairs) {
     // long contractions: 256 x 256 pair tiles (half the operand bytes per flop; the two 256-wide accumulators fill
@@ -889,9 +896,10 @@ using namespace atq;
 extern "C" {
 
 int atq_set_cta_pairs(int enabled) {
-  const int old = (g_cta_pairs ? 1 : 0) | (g_wide_pairs ? 2 : 0);
+  const int old = (g_cta_pairs ? 1 : 0) | (g_wide_pairs ? 2 : 0) | (g_force_pairs ? 8 : 0);
   g_cta_pairs = (enabled & 1) != 0;
   g_wide_pairs = (enabled & 2) != 0 || enabled == 1;
+  g_force_pairs = (enabled & 8) != 0;  // pairs also for problems smaller than one wave (tests of ragged shapes)
   return old;
 }
 

@@ -200,10 +200,11 @@ typedef struct {
  * K8 dX:  dX[N,K] = scale * (dY[N,M] . Bt[K,M]^T); with dot_ref = X it also returns
  *  dot_out = sum(acc .* X) = d(alpha) of TernaryLinear (autograd's sum(G.*T)).
  * Both are this one entry point: D[rows,cols] = scale*(A . B^T) (+bias[cols]).           */
-/* GEMMs with a lo operand part run on CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) when rows >= 256 and
- * cols >= 128 (256 x 256 single-buffered pair tiles when the contraction has >= 32 k-blocks); atq_set_cta_pairs(0) forces
- * the single-CTA kernels, 1 = pairs (default), 4|1 = pairs without the 256-wide tiles (A/B measurements).
- * Returns the previous setting. */
+/* GEMMs with a lo operand part run on CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) when rows >= 256,
+ * cols >= 128 and the problem has at least one 128 x 128 tile per SM (smaller GEMMs are latency bound: single CTAs);
+ * 256 x 256 single-buffered pair tiles when the contraction has >= 32 k-blocks.  atq_set_cta_pairs(0) forces the
+ * single-CTA kernels, 1 = pairs (default), 4|1 = pairs without the 256-wide tiles (A/B measurements), 8|... = pairs also
+ * for problems below one wave (tests of ragged shapes).  Returns the previous setting. */
 int atq_set_cta_pairs(int enabled);
 size_t atq_workspace_bytes_tgemm(int64_t rows, int64_t cols);
 int atq_tgemm(int device, int64_t rows, int64_t cols, int64_t kdim,

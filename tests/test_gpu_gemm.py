@@ -389,3 +389,30 @@ def test_frozen_ternary_linear_is_quantized_once():
         assert len(builds) == n0 + 1
     finally:
         nv.call = orig
+
+
+@pytest.mark.parametrize("rows,cols,k", [(256, 512, 256), (800, 192, 192), (300, 200, 104), (257, 130, 72), (513, 129, 200)])
+def test_cta_pair_kernels_on_ragged_shapes(rows, cols, k):
+    """The cta_group::2 kernels are only selected from one wave of tiles on (smaller GEMMs are latency bound); bit 3 of
+    atq_set_cta_pairs forces them, so their handling of ragged edges (rows % 256, cols % 128, k % 64) stays covered."""
+    import atq._native as nv
+    g = torch.Generator().manual_seed(rows + 3 * cols + 7 * k)
+    a = torch.randn(rows, k, generator=g)
+    b = torch.randn(cols, k, generator=g) / k ** 0.5
+    t = torch.randint(-1, 2, (cols, k), generator=g).float()
+    old = nv.lib.atq_set_cta_pairs(1 | 2 | 8)
+    try:
+        a2, b2 = eng.split_bf16(a.to(DEV), True), eng.split_bf16(b.to(DEV), True)
+        y, _ = eng.tgemm(a2, b2, rows, cols, k)
+        assert torch.allclose(y.cpu().double(), _gemm_ref(a, b), rtol=1e-3, atol=1e-4)
+        y, _ = eng.tgemm(a2, eng.split_bf16(t.to(DEV), False), rows, cols, k)
+        assert torch.allclose(y.cpu().double(), _gemm_ref(a, t), rtol=1e-3, atol=1e-3)
+        # masked dW (MN-major operands read in place): out x in = rows x cols over k tokens
+        dy = torch.randn(k, rows, generator=g)
+        x = torch.randn(k, cols, generator=g)
+        mask = (torch.rand(rows, cols, generator=g) < 0.2).float()
+        dw, _ = eng.tgemm_dw_masked(eng.mn_view(eng.split_bf16(dy.to(DEV), True) + (0, None)),
+                                    eng.mn_view(eng.split_bf16(x.to(DEV), True) + (0, None)), rows, cols, k, mask=mask.to(DEV))
+        assert torch.allclose(dw.cpu().double(), (dy.double().t() @ x.double()) * mask.double(), **TOL)
+    finally:
+        nv.lib.atq_set_cta_pairs(old)
