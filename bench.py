@@ -244,6 +244,14 @@ def cpu_baseline_subprocess(args, workload):
 _LEAD_CYCLES = 3_000_000  # ~1.5 ms at 1.965 GHz
 
 
+def _device_spin(cycles):
+    """Queue a one-thread spin of `cycles` SM clocks on the current stream (no memory traffic).  `torch.cuda._sleep` is a
+    private torch API: without it the timings simply keep the host launch latency they had before."""
+    spin = getattr(torch.cuda, "_sleep", None)
+    if spin is not None:
+        spin(int(cycles))
+
+
 def _event_time(fn, iters, flush=None):
     """Median device time of fn() in ms.  Per iteration: L2 flush, then a device-side spin (`torch.cuda._sleep`, one
     thread, no memory traffic) that the host uses to enqueue fn() completely - tensor allocation, ctypes pointer tables and
@@ -255,7 +263,7 @@ def _event_time(fn, iters, flush=None):
     for _ in range(iters):
         if flush is not None:
             flush()
-        torch.cuda._sleep(_LEAD_CYCLES)
+        _device_spin(_LEAD_CYCLES)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         fn()
@@ -278,7 +286,7 @@ def _event_time_rotating(fn_i, n_bufs, rounds, iters, flush=None):
     for _ in range(iters):
         if flush is not None:
             flush()
-        torch.cuda._sleep(_LEAD_CYCLES)
+        _device_spin(_LEAD_CYCLES)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         keep = [fn_i(i) for _ in range(rounds) for i in range(n_bufs)]
@@ -614,7 +622,7 @@ def measure_workload(args, cfg, steps, warmup, ctx, use_graph, clock_sampler=Non
                 # a launch-bound step (that is why it is graphed): run eagerly, the GPU would idle between launches and each
                 # event pair would bracket host launch latency, not kernel time.  A device-side spin queued ahead of the
                 # pass lets the host enqueue the step first, so the calls execute back to back as they do in the graph.
-                torch.cuda._sleep(int(40e-3 * 1.9e9))
+                _device_spin(40e-3 * 1.9e9)
             eager_step(resident[i % pool])
     summ = prof.summary()
     own_ms = sum(d["ms"] for d in summ.values()) / 2
