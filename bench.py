@@ -298,6 +298,11 @@ def _event_time_rotating(fn_i, n_bufs, rounds, iters, flush=None):
     return times[len(times) // 2]
 
 
+# nominal B200 peaks quoted by BASELINE.json's north_star (report fractions against both; `frac` = measured)
+NOMINAL_HBM_GBS = 8000.0
+NOMINAL_BF16_TFLOPS = 2250.0
+
+
 TIMING_NOTE = ("median of the iterations; CUDA events on the launching stream; L2 flushed before each; host launch latency "
                "hidden behind a 1.5 ms device-side spin queued ahead of the start event")
 
@@ -353,7 +358,9 @@ def gemm_rooflines(device, peaks, flush):
                             "bound": "tensor", "unit": "TFLOP/s", "peak": tf, "peak_kind": f"bf16 burst {src}",
                             "fwd_ms": round(ms_f, 4), "fwd_achieved": round(fl / ms_f / 1e9, 1), "fwd_frac": round(fl / ms_f / 1e9 / tf, 4),
                             "fwdbwd_ms": round(ms_fb, 4), "achieved": round(n_gemm * fl / ms_fb / 1e9, 1),
-                            "frac": round(n_gemm * fl / ms_fb / 1e9 / tf, 4), "traffic": NCU_TRAFFIC.get(key),
+                            "frac": round(n_gemm * fl / ms_fb / 1e9 / tf, 4),
+                            "frac_of_nominal_2250TF": round(n_gemm * fl / ms_fb / 1e9 / NOMINAL_BF16_TFLOPS, 4),
+                            "fwd_frac_of_nominal_2250TF": round(fl / ms_f / 1e9 / NOMINAL_BF16_TFLOPS, 4), "traffic": NCU_TRAFFIC.get(key),
                             "useful_flops": f"{n_gemm} GEMMs x 2*N*K*M (hi/lo terms count 0)"})
             del mod, x, gy, xi
             torch.cuda.empty_cache()
@@ -414,7 +421,8 @@ def streaming_rooflines(device, peaks, flush):
     def rec(kernel, workload, bpe, n, ms, traffic=None, note=None):
         ach = bpe * n / (ms * 1e-3) / 1e9
         r = {"kernel": kernel, "workload": workload, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm, "unit": "GB/s",
-             "frac": round(ach / hbm, 4), "peak_kind": f"copy {src}", "ms": round(ms, 4), "alg_bytes_per_elem": bpe, "traffic": traffic}
+             "frac": round(ach / hbm, 4), "frac_of_nominal_8TBs": round(ach / NOMINAL_HBM_GBS, 4), "peak_kind": f"copy {src}",
+             "ms": round(ms, 4), "alg_bytes_per_elem": bpe, "traffic": traffic}
         if note:
             r["note"] = note
         out.append(r)
